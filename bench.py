@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the APT decode hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of decode() (resample -> envelope -> low-pass -> sync -> rows) over one
+synthetic recording per GPU.  Workload at every N: BASELINE.json configs[1], a single synthetic
+48 kHz, 15-min, 2.4 kHz-subcarrier APT recording (43.2 M samples) per GPU ("weak" scaling: each
+rank decodes its own recording, no collective on the data path).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference        # CPU arm: the oracle port of the Rust reference
+
+JSON keys beyond the base contract: roofline (dominant kernel, CUDA-event timed on the decoder's
+stream), cpu_baseline (oracle on the host cores), e2e (host buffers through the C ABI), clocks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "input_msamples_per_s_decoded"
+UNIT = "Msamples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rate", type=int, default=48000, help="input sample rate (Hz)")
+    ap.add_argument("--seconds", type=float, default=900.0, help="recording length")
+    ap.add_argument("--cpu-seconds", type=float, default=180.0,
+                    help="length of the recording slice the CPU arms decode per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_recording(rate, seconds, seed):
+    from noaa_apt_b200 import synth
+    return synth.apt_pcm16(rate, seconds, seed=seed)
+
+
+def cpu_arm(pcm, rate, steps, warmup):
+    """Times the CPU oracle (C restatement of the Rust reference, 1 thread like the reference)."""
+    import oracle
+    x = pcm.astype(np.float32)
+    for _ in range(warmup):
+        oracle.decode(x, rate)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.decode(x, rate)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return x.size / dt / 1e6, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port: the Rust crate cannot be built
+    here) on the host cores, same config/metric, each step a bounded slice of the workload."""
+    if rank != 0:
+        return
+    pcm = make_recording(args.rate, min(args.cpu_seconds, args.seconds), seed=0)
+    value, dt = cpu_arm(pcm, args.rate, args.steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"single synthetic {args.rate} Hz {args.seconds:g}-s APT recording (BASELINE configs[1])",
+                   "profile": "standard"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"first {min(args.cpu_seconds, args.seconds):g} s of the recording per step; "
+                                   f"C restatement of the single-threaded Rust decode (no Rust toolchain in the image)",
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import noaa_apt_b200 as na
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    rate, K, W = args.rate, args.steps, max(args.warmup, 3)
+    pcm = make_recording(rate, args.seconds, seed=rank)
+    n = pcm.size
+    settings = na.Settings()
+    dec = na.Decoder(rate, settings, max_samples=n, device=local_rank)
+    bound = dec.out_bound(n)
+
+    # ---- device-resident arm ("value"): the Signal (f32, wav.rs:37) already in HBM ----
+    x_host = torch.from_numpy(pcm.astype(np.float32)).pin_memory()
+    x_dev = x_host.to(f"cuda:{local_rank}")
+    out_dev = torch.empty(bound, dtype=torch.float32, device=f"cuda:{local_rank}")
+    stream = torch.cuda.ExternalStream(dec.stream, device=local_rank)
+
+    def step_device():
+        dec.submit_device(x_dev.data_ptr(), na._lib.F32, n, True, out_dev.data_ptr(), bound)
+        return dec.wait()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = dec.launch_count
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if dist_on:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), dec.launch_count - l0
+
+    for _ in range(W):
+        produced = step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total, launches = timed(step_device, K)
+    clocks = sampler.stop()
+    ms_step = ms_total / K
+    value = world * n / (ms_step * 1e-3) / 1e6
+
+    # ---- end-to-end arm: host buffers through the reference-facing call (H2D + D2H inside) ----
+    out_host = torch.empty(bound, dtype=torch.float32).pin_memory()
+
+    def step_host():
+        dec.submit_host_ptr(x_host.data_ptr(), na._lib.F32, n, True, out_host.data_ptr(), bound)
+        return dec.wait()
+
+    for _ in range(2):
+        produced_host = step_host()
+    e2e_ms_total, _ = timed(step_host, K)
+    e2e_ms = e2e_ms_total / K
+    e2e_value = world * n / (e2e_ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel: CUDA events on the decoder's stream, per launch ----
+    dec.set_profiling(True)
+    acc = {}
+    prof_steps = min(K, 10)
+    for _ in range(prof_steps):
+        step_device()
+        for name, ms in dec.kernel_times_ms():
+            acc.setdefault(name, []).append(ms)
+    dec.set_profiling(False)
+    kernel_ms = {k: float(np.mean(v)) for k, v in acc.items()}
+    counts = dec.last_counts()
+    n_work = counts["n_work"]
+    peak, peak_kind = measured_peaks()
+    dom = "resample_envelope"
+    alg_bytes = 4 * n + 4 * n_work                      # read every input once, write every e once
+    achieved = alg_bytes / (kernel_ms[dom] * 1e-3) / 1e9 if dom in kernel_ms else None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_kind,
+                "algorithmic_bytes": alg_bytes, "kernel_ms": kernel_ms.get(dom),
+                "all_kernels_ms": kernel_ms}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            sl = pcm[: int(min(args.cpu_seconds, args.seconds) * rate)]
+            v, dt = cpu_arm(sl, rate, steps=3, warmup=1)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"first {sl.size / rate:g} s of the same recording, 3 timed decodes; C restatement of the "
+                             f"single-threaded Rust decode", "host_cores_available": os.cpu_count()}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"single synthetic {rate} Hz {args.seconds:g}-s APT recording per GPU "
+                                   f"(BASELINE configs[1])", "profile": "standard", "samples_per_recording": int(n),
+                       "work_samples": int(n_work), "rows": int(produced // 2080),
+                       "l2": "inputs_exceed_l2 (172.8 MB f32 input per step > 126 MB L2)",
+                       "sharding": "one recording per GPU, no collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(4 * n),
+                    "d2h_bytes_per_step": int(4 * produced_host + 32), "input": "pinned host f32 Signal"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    dec.close()
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

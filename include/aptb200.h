@@ -1,0 +1,226 @@
+/*
+ * aptb200.h -- C ABI of the B200-native APT decode path.
+ *
+ * Drop-in boundary for the signal-to-image hot path of martinber/noaa-apt
+ * v1.4.1 (src/{dsp,filters,decode,resample}.rs).  The reference has no FFI
+ * boundary today (it is a single Rust binary crate), so every entry point
+ * below names the Rust function whose body it replaces; the Rust-side shim
+ * that binds them is in rust/ and INTEGRATION.md.  All signatures are plain
+ * C: pointers, sizes, PODs -- no CUDA, torch or C++ types.
+ *
+ * Conventions
+ *   - "host" entry points take ordinary host pointers, are synchronous and
+ *     re-entrant (no hidden global state; each call picks its CUDA device).
+ *   - `apt_decoder` is the explicit-state variant: it owns a device, a stream,
+ *     device workspaces and pinned staging, and offers submit/wait so that a
+ *     batch of independent recordings can be kept in flight one per stream.
+ *   - Every function returns an `apt_status`.  A short human-readable message
+ *     for the last failure on the calling thread is in apt_last_error().
+ *   - There is NO CPU fallback: without a usable CUDA device the compute entry
+ *     points fail with APT_ERR_CUDA.
+ *   - Arithmetic is f32 like the reference; results match the reference's
+ *     scalar CPU path to <= 1e-5 of the stage's max |value| (FMA contraction
+ *     is the only difference), and sync positions match exactly.
+ */
+#ifndef APTB200_H
+#define APTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APTB200_ABI_VERSION 1
+
+/* ---------------------------------------------------------------- status */
+
+/* Maps onto err::Error (err.rs:9-44).  1-4 are the four Error::Internal
+ * conditions reachable on this path, 5 is Error::RateOverflow. */
+typedef enum apt_status {
+    APT_OK = 0,
+    APT_ERR_RESAMPLE_TO_ZERO = 1, /* Internal("Can't resample to 0Hz")              dsp.rs:69-71     */
+    APT_ERR_TOO_SHORT = 2,        /* Internal("Got less than 10 rows of samples..") decode.rs:79-83  */
+    APT_ERR_FEW_SYNC_FRAMES = 3,  /* Internal("Found less than 5 sync frames...")   decode.rs:112-118*/
+    APT_ERR_WORK_RATE = 4,        /* Internal("work_rate is not multiple of ...")   decode.rs:172-176*/
+    APT_ERR_RATE_OVERFLOW = 5,    /* RateOverflow(...)                               dsp.rs:82-91     */
+    APT_ERR_CUDA = 6,             /* CUDA runtime/driver failure, or no device (no CPU fallback)      */
+    APT_ERR_BAD_ARG = 7,          /* inputs on which the reference panics (empty signal dsp.rs:367,
+                                     even Kaiser window filters.rs:68-70, rate 0) or NULL pointers    */
+    APT_ERR_NOMEM = 8,            /* host or device allocation failed                                 */
+    APT_ERR_CAPACITY = 9,         /* caller's output buffer is too small (required size returned)     */
+    APT_ERR_EMPTY_RESULT = 10     /* Internal("Got zero samples after resampling...") resample.rs:46-52 */
+} apt_status;
+
+const char *apt_strerror(int status);
+/* Message of the last failure on this thread ("" if none); valid until the next call on this thread. */
+const char *apt_last_error(void);
+int apt_abi_version(void);
+/* Number of usable CUDA devices (0 if none / no driver).  Never fails. */
+int apt_device_count(void);
+
+/* -------------------------------------------------------------- settings */
+
+/* The DSP fields of config::Settings (config.rs:85-98) -- the only part of the
+ * settings that crosses the boundary (read at decode.rs:55-75,98). */
+typedef struct apt_settings {
+    uint32_t work_rate;           /* Hz */
+    float resample_atten;         /* dB, positive */
+    float resample_delta_freq;    /* Hz */
+    float resample_cutout;        /* Hz */
+    float demodulation_atten;     /* dB, positive */
+} apt_settings;
+
+/* "standard" profile, default_settings.toml:108-116. */
+void apt_default_settings(apt_settings *s);
+/* profile: "standard" | "fast" | "slow" (default_settings.toml:108-140). */
+int apt_profile_settings(const char *profile, apt_settings *s);
+
+/* --------------------------------------------------------------- filters */
+
+/* filters.rs:18-46.  Frequencies are Freq values in fractions of pi rad/sample
+ * (Freq::get_pi_rad, frequency.rs:80-82). */
+typedef enum apt_filter_kind {
+    APT_FILTER_NONE = 0,          /* filters::NoFilter          */
+    APT_FILTER_LOWPASS = 1,       /* filters::Lowpass           */
+    APT_FILTER_LOWPASS_DC = 2     /* filters::LowpassDcRemoval  */
+} apt_filter_kind;
+
+typedef struct apt_filter {
+    int kind;                     /* apt_filter_kind */
+    float cutout_pi;              /* cutout.get_pi_rad()  */
+    float atten;                  /* dB, positive         */
+    float delta_w_pi;             /* delta_w.get_pi_rad() */
+} apt_filter;
+
+/* Freq::hz(f, rate).get_pi_rad() -- frequency.rs:68-72. */
+float apt_freq_hz(float f_hz, uint32_t rate_hz);
+/* misc::bessel_i0 -- misc.rs:47-57. */
+float apt_bessel_i0(float x);
+/* Filter::resample(input_rate, output_rate) -- filters.rs:90-94,134-138 (no-op for NoFilter). */
+void apt_filter_resample(apt_filter *f, uint32_t input_rate, uint32_t output_rate);
+/* Filter::design() -- filters.rs:49-51,57-88,98-132 (+ kaiser :144-183).  Host code, no GPU.
+ * Writes min(*n, cap) taps to out (out may be NULL when cap == 0) and the tap count to *n. */
+int apt_filter_design(const apt_filter *f, float *out, size_t cap, size_t *n);
+
+/* -------------------------------------------- stage entry points (host) */
+
+/* Output length of dsp::resample_with_filter for `n` input samples (exact). */
+int apt_resample_len(uint64_t n, uint32_t input_rate, uint32_t output_rate, const apt_filter *f,
+                     uint64_t *nout);
+
+/* dsp::resample_with_filter -- dsp.rs:62-126 (polyphase fast_resampling :186-289 when L > 1,
+ * filter + decimate :105-123 when L == 1). */
+int apt_resample_with_filter(const float *signal, uint64_t n, uint32_t input_rate, uint32_t output_rate,
+                             const apt_filter *f, float *out, uint64_t cap, uint64_t *nout);
+
+/* dsp::resample -- dsp.rs:132-162 (Lowpass with cutout = min(in,out)/2); the WAV->WAV tool path. */
+int apt_resample(const float *signal, uint64_t n, uint32_t input_rate, uint32_t output_rate,
+                 float atten, float delta_w_pi, float *out, uint64_t cap, uint64_t *nout);
+
+/* dsp::demodulate -- dsp.rs:350-383.  carrier_pi = carrier_freq.get_pi_rad(). */
+int apt_demodulate(const float *signal, uint64_t n, float carrier_pi, float *out);
+
+/* dsp::filter -- dsp.rs:386-410 (causal, strict i > j). */
+int apt_filter_signal(const float *signal, uint64_t n, const apt_filter *f, float *out);
+/* Same with explicit coefficients. */
+int apt_filter_taps(const float *signal, uint64_t n, const float *coeff, size_t ncoeff, float *out);
+
+/* decode::generate_sync_frame -- decode.rs:171-199. */
+int apt_generate_sync_frame(uint32_t work_rate, int8_t *out, size_t cap, size_t *n);
+
+/* decode::find_sync -- decode.rs:204-263.  If corr != NULL it receives the n - guard_len
+ * cross-correlation values (the Context::export_steps branch, decode.rs:235-237). */
+int apt_find_sync(const float *signal, uint64_t n, uint32_t work_rate,
+                  uint64_t *positions, size_t cap, size_t *npositions, float *corr);
+
+/* ------------------------------------------------------- decode (host) */
+
+/* Context::status(progress, description) -- context.rs:127-129.  Fired on the calling thread
+ * at the reference's five points (decode.rs:63,87,93,107/136,154). */
+typedef void (*apt_status_cb)(float progress, const char *description, void *user);
+
+/* Upper bound, in floats, of decode()'s output for n input samples (rows * 2080). */
+int apt_decode_len_bound(uint64_t n, uint32_t input_rate, const apt_settings *s, uint64_t *bound);
+
+/* noaa_apt::decode == decode::decode -- decode.rs:43-162.
+ * out receives rows*2080 f32 pixels; *nout the count.  cap in floats. */
+int apt_decode(const float *signal, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
+               float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user);
+
+/* Same, taking the PCM16 samples of the WAV directly: the `as f32` cast of wav::load_wav
+ * (wav.rs:31-40) is fused into the resampler's load, halving the host->device bytes. */
+int apt_decode_pcm16(const int16_t *pcm, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
+                     float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user);
+
+/* ----------------------------------------------- decoder object (streams) */
+
+typedef struct apt_decoder apt_decoder;
+
+typedef enum apt_sample_format { APT_F32 = 0, APT_PCM16 = 1 } apt_sample_format;
+
+/* Creates a decoder bound to CUDA device `device` for recordings of `input_rate` Hz of up to
+ * `max_samples` samples.  Designs both filters, uploads the taps and allocates every workspace
+ * (nothing is allocated afterwards). */
+int apt_decoder_create(int device, uint32_t input_rate, const apt_settings *s, uint64_t max_samples,
+                       apt_decoder **dec);
+void apt_decoder_destroy(apt_decoder *dec);
+
+/* Enqueue one decode on the decoder's stream and return immediately.
+ *   *_device: `signal` and `out` are device pointers on the decoder's device (inputs resident in HBM).
+ *   *_host:   host pointers; the H2D of the samples and the D2H of the rows are part of the job
+ *             (asynchronous when the buffers are pinned, e.g. from apt_host_alloc).
+ * `cap` is the capacity of `out` in floats (>= apt_decode_len_bound).  One job in flight per decoder. */
+int apt_decoder_submit_device(apt_decoder *dec, const void *signal, int format, uint64_t n, int sync,
+                              float *out, uint64_t cap);
+int apt_decoder_submit_host(apt_decoder *dec, const void *signal, int format, uint64_t n, int sync,
+                            float *out, uint64_t cap);
+/* Block until the job is finished; returns its status (APT_ERR_FEW_SYNC_FRAMES etc.) and *nout. */
+int apt_decoder_wait(apt_decoder *dec, uint64_t *nout);
+
+/* Introspection after a wait(): sync positions found (decode.rs:110), N_w, rows. */
+int apt_decoder_last_sync(apt_decoder *dec, uint64_t *positions, size_t cap, size_t *npositions);
+int apt_decoder_last_counts(apt_decoder *dec, uint64_t *n_work, uint64_t *n_rows, uint64_t *n_peaks);
+/* Copy an intermediate signal of the last job back to the host (what Context::step would dump):
+ * which = 0 "demodulation_result" input i.e. resample+envelope output, 1 "filter_result",
+ * 2 "sync_correlation". */
+int apt_decoder_read_stage(apt_decoder *dec, int which, float *out, uint64_t cap, uint64_t *n);
+
+/* Per-kernel device time of the LAST job in milliseconds (CUDA events on the decoder's stream);
+ * enable before submitting.  Names via apt_decoder_kernel_name(i).  Profiling adds event records
+ * to the stream, so use it for roofline accounting, not inside a throughput measurement. */
+int apt_decoder_set_profiling(apt_decoder *dec, int enabled);
+int apt_decoder_kernel_count(apt_decoder *dec);
+const char *apt_decoder_kernel_name(apt_decoder *dec, int i);
+int apt_decoder_kernel_ms(apt_decoder *dec, float *ms, int cap, int *count);
+/* The decoder's cudaStream_t, as an opaque pointer (for event timing by the caller). */
+void *apt_decoder_stream(apt_decoder *dec);
+/* Kernel launches issued by this decoder since creation. */
+uint64_t apt_decoder_launch_count(apt_decoder *dec);
+
+/* Pinned host memory for asynchronous submit_host (cudaHostAlloc / cudaFreeHost). */
+int apt_host_alloc(void **ptr, size_t bytes);
+void apt_host_free(void *ptr);
+/* Device memory on `device` (cudaMalloc / cudaFree) for submit_device users without a CUDA binding. */
+int apt_device_alloc(int device, void **ptr, size_t bytes);
+void apt_device_free(int device, void *ptr);
+int apt_memcpy_h2d(int device, void *dst, const void *src, size_t bytes);
+int apt_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
+
+/* ------------------------------------------------------------------ batch */
+
+/* Decode `count` independent recordings (all at `input_rate`, same settings), sharded
+ * recording i -> device devices[i % ndevices], streams_per_device jobs in flight per device,
+ * no inter-device communication.  signals[i]/lens[i] are host buffers; outs[i] (capacity caps[i]
+ * floats) receive the rows, nouts[i] the counts and statuses[i] the per-recording status.
+ * Returns APT_OK if every recording decoded, else the first failing status. */
+int apt_decode_batch(const void *const *signals, int format, const uint64_t *lens, int count,
+                     uint32_t input_rate, const apt_settings *s, int sync,
+                     float *const *outs, const uint64_t *caps, uint64_t *nouts, int *statuses,
+                     const int *devices, int ndevices, int streams_per_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APTB200_H */

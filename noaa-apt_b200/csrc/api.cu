@@ -1,0 +1,714 @@
+// C ABI (include/aptb200.h) over the decoder object and the stage kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "aptb200.h"
+#include "common.hpp"
+#include "decoder.hpp"
+#include "filters_host.hpp"
+#include "launch.hpp"
+
+using namespace aptb200;
+
+namespace aptb200 {
+int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int sync, float *rows_out);
+int run_find_sync(apt_decoder *d, uint64_t nwork);
+}  // namespace aptb200
+
+namespace {
+
+inline size_t sample_bytes(int format) { return format == APT_PCM16 ? 2 : 4; }
+
+// RAII device buffer for the one-shot stage entry points.
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t bytes) {
+        APT_CUDA(cudaMalloc(&p, bytes ? bytes : 4));
+        return APT_OK;
+    }
+    template <typename T>
+    T *as() const { return static_cast<T *>(p); }
+};
+
+int require_device() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(APT_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    return APT_OK;
+}
+
+int free_decoder_buffers(apt_decoder *d) {
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    for (void *p : {(void *)d->d_h, (void *)d->d_lp, (void *)d->d_one, (void *)d->d_guard, d->d_in, (void *)d->d_r,
+                    (void *)d->d_e, (void *)d->d_f, (void *)d->d_corr, (void *)d->d_aligned, (void *)d->d_root_list,
+                    (void *)d->d_root_count, (void *)d->d_pos, (void *)d->d_res, (void *)d->d_out})
+        if (p) cudaFree(p);
+    if (d->h_res) cudaFreeHost(d->h_res);
+    for (auto e : d->ev_begin) cudaEventDestroy(e);
+    for (auto e : d->ev_end) cudaEventDestroy(e);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    return APT_OK;
+}
+
+// Allocates what find_sync needs for up to max_work work-rate samples.
+int alloc_sync_buffers(apt_decoder *d) {
+    const Plan &p = d->plan;
+    if (!p.work_multiple || d->max_work <= p.guard.size()) return APT_OK;
+    d->max_corr = d->max_work - p.guard.size();
+    d->max_blocks = static_cast<uint32_t>((d->max_corr + p.dist - 1) / p.dist);
+    d->max_positions = static_cast<uint32_t>(d->max_work / p.row + 2);
+    APT_CUDA(cudaMalloc(&d->d_guard, p.guard.size()));
+    APT_CUDA(cudaMemcpy(d->d_guard, p.guard.data(), p.guard.size(), cudaMemcpyHostToDevice));
+    APT_CUDA(cudaMalloc(&d->d_corr, d->max_corr * sizeof(float)));
+    APT_CUDA(cudaMalloc(&d->d_root_list, static_cast<size_t>(d->max_blocks) * p.dist * sizeof(u32)));
+    APT_CUDA(cudaMalloc(&d->d_root_count, static_cast<size_t>(d->max_blocks) * sizeof(u32)));
+    APT_CUDA(cudaMalloc(&d->d_pos, static_cast<size_t>(d->max_positions) * sizeof(u32)));
+    return APT_OK;
+}
+
+}  // namespace
+
+// ============================================================================ misc / status
+
+extern "C" const char *apt_strerror(int status) {
+    switch (status) {
+    case APT_OK: return "ok";
+    case APT_ERR_RESAMPLE_TO_ZERO: return "Can't resample to 0Hz";
+    case APT_ERR_TOO_SHORT: return "Got less than 10 rows of samples, audio file is too short";
+    case APT_ERR_FEW_SYNC_FRAMES: return "Found less than 5 sync frames, audio file is too short or too noisy";
+    case APT_ERR_WORK_RATE: return "work_rate is not multiple of FINAL_RATE";
+    case APT_ERR_RATE_OVERFLOW: return "Can't resample, looks like the sample rates do not have a big divisor in common";
+    case APT_ERR_CUDA: return "CUDA error or no CUDA device (no CPU fallback)";
+    case APT_ERR_BAD_ARG: return "invalid argument";
+    case APT_ERR_NOMEM: return "out of memory";
+    case APT_ERR_CAPACITY: return "output buffer too small";
+    case APT_ERR_EMPTY_RESULT: return "Got zero samples after resampling, audio file too short or output sampling frequency too low";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char *apt_last_error(void) { return last_error_slot().c_str(); }
+extern "C" int apt_abi_version(void) { return APTB200_ABI_VERSION; }
+
+extern "C" int apt_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
+extern "C" void apt_default_settings(apt_settings *s) {
+    if (!s) return;
+    // default_settings.toml:108-116
+    s->work_rate = 12480;
+    s->resample_atten = 30.f;
+    s->resample_delta_freq = 1000.f;
+    s->resample_cutout = 4800.f;
+    s->demodulation_atten = 25.f;
+}
+
+extern "C" int apt_profile_settings(const char *profile, apt_settings *s) {
+    if (!profile || !s) return fail(APT_ERR_BAD_ARG, "null argument");
+    if (!strcmp(profile, "standard")) {
+        apt_default_settings(s);
+    } else if (!strcmp(profile, "fast")) {      // default_settings.toml:120-128
+        *s = apt_settings{16640, 30.f, 3000.f, 4800.f, 23.f};
+    } else if (!strcmp(profile, "slow")) {      // default_settings.toml:132-140
+        *s = apt_settings{20800, 40.f, 500.f, 4800.f, 25.f};
+    } else {
+        return fail(APT_ERR_BAD_ARG, "unknown profile '%s'", profile);
+    }
+    return APT_OK;
+}
+
+// ================================================================================ filters
+
+extern "C" float apt_freq_hz(float f_hz, uint32_t rate_hz) { return Freq::hz(f_hz, rate_hz).get_pi_rad(); }
+extern "C" float apt_bessel_i0(float x) { return bessel_i0(x); }
+
+extern "C" void apt_filter_resample(apt_filter *f, uint32_t input_rate, uint32_t output_rate) {
+    if (f) resample_filter(*f, input_rate, output_rate);
+}
+
+extern "C" int apt_filter_design(const apt_filter *f, float *out, size_t cap, size_t *n) {
+    if (!f || !n) return fail(APT_ERR_BAD_ARG, "null argument");
+    std::vector<float> taps;
+    int st = design(*f, taps);
+    if (st != APT_OK) return fail(st, "filter cannot be designed (kind %d, atten %g, delta_w %g)", f->kind,
+                                  (double)f->atten, (double)f->delta_w_pi);
+    *n = taps.size();
+    if (out && cap) memcpy(out, taps.data(), std::min(cap, taps.size()) * sizeof(float));
+    return APT_OK;
+}
+
+extern "C" int apt_generate_sync_frame(uint32_t work_rate, int8_t *out, size_t cap, size_t *n) {
+    if (!n) return fail(APT_ERR_BAD_ARG, "null argument");
+    std::vector<int8_t> g;
+    int st = sync_frame(work_rate, g);
+    if (st != APT_OK) return fail(st, "work_rate is not multiple of FINAL_RATE");
+    *n = g.size();
+    if (out && cap) memcpy(out, g.data(), std::min(cap, g.size()));
+    return APT_OK;
+}
+
+// ============================================================================ stage: resample
+
+namespace {
+
+struct ResamplePlan {
+    Ratio r{};
+    bool polyphase = false;
+    std::vector<float> taps;
+    uint64_t nout = 0;
+};
+
+int plan_resample(uint64_t n, uint32_t in_rate, uint32_t out_rate, const apt_filter *f, ResamplePlan &rp) {
+    if (!f) return fail(APT_ERR_BAD_ARG, "null filter");
+    int st = resample_ratio(in_rate, out_rate, rp.r);
+    if (st == APT_ERR_RESAMPLE_TO_ZERO) return fail(st, "Can't resample to 0Hz");
+    if (st == APT_ERR_RATE_OVERFLOW)
+        return fail(st, "Can't resample, looks like the sample rates do not have a big divisor in common. "
+                        "input_rate: %u, output_rate: %u, l: %u, m: %u", in_rate, out_rate, rp.r.l, rp.r.m);
+    if (st != APT_OK) return fail(st, "invalid input rate");
+    rp.polyphase = rp.r.l > 1;
+    apt_filter ff = *f;
+    if (rp.polyphase) resample_filter(ff, in_rate, in_rate * rp.r.l);
+    st = design(ff, rp.taps);
+    if (st != APT_OK) return fail(st, "filter cannot be designed");
+    rp.nout = rp.polyphase ? polyphase_len(n, rp.r.l, rp.r.m, rp.taps.size()) : n / rp.r.m;
+    return APT_OK;
+}
+
+}  // namespace
+
+extern "C" int apt_resample_len(uint64_t n, uint32_t input_rate, uint32_t output_rate, const apt_filter *f,
+                                uint64_t *nout) {
+    if (!nout) return fail(APT_ERR_BAD_ARG, "null argument");
+    ResamplePlan rp;
+    APT_TRY(plan_resample(n, input_rate, output_rate, f, rp));
+    *nout = rp.nout;
+    return APT_OK;
+}
+
+extern "C" int apt_resample_with_filter(const float *signal, uint64_t n, uint32_t input_rate, uint32_t output_rate,
+                                        const apt_filter *f, float *out, uint64_t cap, uint64_t *nout) {
+    if (!nout || (!signal && n)) return fail(APT_ERR_BAD_ARG, "null argument");
+    ResamplePlan rp;
+    APT_TRY(plan_resample(n, input_rate, output_rate, f, rp));
+    *nout = rp.nout;
+    if (rp.nout > cap || (!out && rp.nout)) return fail(APT_ERR_CAPACITY, "output needs %llu floats", (unsigned long long)rp.nout);
+    if (rp.nout == 0) return APT_OK;
+    APT_TRY(require_device());
+    DevBuf dx, dh, dy;
+    APT_TRY(dx.alloc(n * sizeof(float)));
+    APT_TRY(dh.alloc(rp.taps.size() * sizeof(float)));
+    APT_TRY(dy.alloc(rp.nout * sizeof(float)));
+    APT_CUDA(cudaMemcpy(dx.p, signal, n * sizeof(float), cudaMemcpyHostToDevice));
+    APT_CUDA(cudaMemcpy(dh.p, rp.taps.data(), rp.taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const LaunchCtx c{nullptr, 148};
+    if (rp.polyphase) {
+        const uint64_t off2 = 2 * ((static_cast<uint64_t>(rp.taps.size()) - 1) / 2);
+        APT_TRY(launch_polyphase(c, dx.p, APT_F32, n, dh.as<float>(), rp.r.l, rp.r.m, off2, rp.nout, false, 0.f, 1.f,
+                                 dy.as<float>()));
+    } else {
+        APT_TRY(launch_fir_decimate(c, dx.p, APT_F32, dh.as<float>(), static_cast<u32>(rp.taps.size()), rp.r.m,
+                                    rp.nout, dy.as<float>()));
+    }
+    APT_CUDA(cudaMemcpy(out, dy.p, rp.nout * sizeof(float), cudaMemcpyDeviceToHost));
+    return APT_OK;
+}
+
+extern "C" int apt_resample(const float *signal, uint64_t n, uint32_t input_rate, uint32_t output_rate, float atten,
+                            float delta_w_pi, float *out, uint64_t cap, uint64_t *nout) {
+    if (input_rate == 0) return fail(APT_ERR_BAD_ARG, "invalid input rate");
+    // dsp.rs:140-149: keep what fits below the lower of the two Nyquist frequencies
+    const float cut_hz = output_rate > input_rate ? static_cast<float>(input_rate) / 2.f
+                                                  : static_cast<float>(output_rate) / 2.f;
+    apt_filter f{APT_FILTER_LOWPASS, Freq::hz(cut_hz, input_rate).get_pi_rad(), atten, delta_w_pi};
+    return apt_resample_with_filter(signal, n, input_rate, output_rate, &f, out, cap, nout);
+}
+
+// ===================================================================== stage: demod / filter
+
+extern "C" int apt_demodulate(const float *signal, uint64_t n, float carrier_pi, float *out) {
+    if (n == 0) return fail(APT_ERR_BAD_ARG, "empty signal");   // signal[0] panics, dsp.rs:367
+    if (!signal || !out) return fail(APT_ERR_BAD_ARG, "null argument");
+    APT_TRY(require_device());
+    const float phi = 2.f * Freq::pi_rad(carrier_pi).get_rad();
+    const float cosphi2 = std::cos(phi) * 2.f;
+    const float sinphi = std::sin(phi);
+    DevBuf dx, dy;
+    APT_TRY(dx.alloc(n * sizeof(float)));
+    APT_TRY(dy.alloc(n * sizeof(float)));
+    APT_CUDA(cudaMemcpy(dx.p, signal, n * sizeof(float), cudaMemcpyHostToDevice));
+    APT_TRY(launch_envelope(LaunchCtx{nullptr, 148}, dx.as<float>(), n, cosphi2, sinphi, dy.as<float>()));
+    APT_CUDA(cudaMemcpy(out, dy.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return APT_OK;
+}
+
+extern "C" int apt_filter_taps(const float *signal, uint64_t n, const float *coeff, size_t ncoeff, float *out) {
+    if ((!signal || !out) && n) return fail(APT_ERR_BAD_ARG, "null argument");
+    if (!coeff && ncoeff) return fail(APT_ERR_BAD_ARG, "null coefficients");
+    if (n == 0) return APT_OK;
+    APT_TRY(require_device());
+    DevBuf dx, dc, dy;
+    APT_TRY(dx.alloc(n * sizeof(float)));
+    APT_TRY(dc.alloc(ncoeff * sizeof(float)));
+    APT_TRY(dy.alloc(n * sizeof(float)));
+    APT_CUDA(cudaMemcpy(dx.p, signal, n * sizeof(float), cudaMemcpyHostToDevice));
+    if (ncoeff) APT_CUDA(cudaMemcpy(dc.p, coeff, ncoeff * sizeof(float), cudaMemcpyHostToDevice));
+    APT_TRY(launch_fir_decimate(LaunchCtx{nullptr, 148}, dx.p, APT_F32, dc.as<float>(), static_cast<u32>(ncoeff), 1, n,
+                                dy.as<float>()));
+    APT_CUDA(cudaMemcpy(out, dy.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return APT_OK;
+}
+
+extern "C" int apt_filter_signal(const float *signal, uint64_t n, const apt_filter *f, float *out) {
+    if (!f) return fail(APT_ERR_BAD_ARG, "null filter");
+    std::vector<float> taps;
+    int st = design(*f, taps);
+    if (st != APT_OK) return fail(st, "filter cannot be designed");
+    return apt_filter_taps(signal, n, taps.data(), taps.size(), out);
+}
+
+// ============================================================================ stage: find_sync
+
+extern "C" int apt_find_sync(const float *signal, uint64_t n, uint32_t work_rate, uint64_t *positions, size_t cap,
+                             size_t *npositions, float *corr) {
+    if (!signal || !npositions) return fail(APT_ERR_BAD_ARG, "null argument");
+    apt_decoder d;   // a decoder shell that only owns the sync workspaces
+    d.plan.st.work_rate = work_rate;
+    int st = sync_frame(work_rate, d.plan.guard);
+    if (st != APT_OK) return fail(st, "work_rate is not multiple of FINAL_RATE");
+    if (work_rate > UINT32_MAX / kPxPerRow) return fail(APT_ERR_BAD_ARG, "work_rate too large");
+    d.plan.work_multiple = true;
+    d.plan.row = kPxPerRow * work_rate / kFinalRate;
+    d.plan.dist = static_cast<uint32_t>(static_cast<uint64_t>(d.plan.row) * 8 / 10);
+    if (n < d.plan.guard.size()) return fail(APT_ERR_BAD_ARG, "signal shorter than the sync frame");   // decode.rs:225 underflow
+    if (n >= (1ull << 32)) return fail(APT_ERR_BAD_ARG, "signal too long");
+    APT_TRY(require_device());
+    struct Guard {
+        apt_decoder *d;
+        ~Guard() { free_decoder_buffers(d); }
+    } guard{&d};
+    APT_CUDA(cudaGetDevice(&d.device));
+    APT_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    d.max_work = n;
+    size_t got = 0;
+    if (n == d.plan.guard.size()) {
+        // empty correlation: the peak list is just the seed (0, 0.0) (decode.rs:208-209)
+        if (positions && cap > 0) positions[0] = 0;
+        *npositions = 1;
+        return APT_OK;
+    }
+    APT_TRY(alloc_sync_buffers(&d));
+    APT_CUDA(cudaMalloc(&d.d_f, n * sizeof(float)));
+    APT_CUDA(cudaMalloc(&d.d_res, sizeof(SyncResult)));
+    APT_CUDA(cudaMemsetAsync(d.d_res, 0, sizeof(SyncResult), d.stream));
+    APT_CUDA(cudaMemcpyAsync(d.d_f, signal, n * sizeof(float), cudaMemcpyHostToDevice, d.stream));
+    APT_TRY(run_find_sync(&d, n));
+    SyncResult res;
+    APT_CUDA(cudaMemcpyAsync(&res, d.d_res, sizeof(res), cudaMemcpyDeviceToHost, d.stream));
+    APT_CUDA(cudaStreamSynchronize(d.stream));
+    got = res.n_peaks;
+    *npositions = got;
+    if (positions) {
+        std::vector<u32> tmp(got);
+        APT_CUDA(cudaMemcpy(tmp.data(), d.d_pos, got * sizeof(u32), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < std::min(got, cap); ++i) positions[i] = tmp[i];
+    }
+    if (corr) APT_CUDA(cudaMemcpy(corr, d.d_corr, (n - d.plan.guard.size()) * sizeof(float), cudaMemcpyDeviceToHost));
+    if (positions && got > cap) return fail(APT_ERR_CAPACITY, "positions needs %zu entries", got);
+    return APT_OK;
+}
+
+// ================================================================================= decoder
+
+extern "C" int apt_decode_len_bound(uint64_t n, uint32_t input_rate, const apt_settings *s, uint64_t *bound) {
+    if (!s || !bound) return fail(APT_ERR_BAD_ARG, "null argument");
+    Plan p;
+    APT_TRY(make_plan(input_rate, *s, p));
+    *bound = plan_out_bound(p, n);
+    return APT_OK;
+}
+
+extern "C" int apt_decoder_create(int device, uint32_t input_rate, const apt_settings *s, uint64_t max_samples,
+                                  apt_decoder **dec) {
+    if (!s || !dec) return fail(APT_ERR_BAD_ARG, "null argument");
+    *dec = nullptr;
+    std::unique_ptr<apt_decoder> d(new (std::nothrow) apt_decoder);
+    if (!d) return fail(APT_ERR_NOMEM, "out of host memory");
+    APT_TRY(make_plan(input_rate, *s, d->plan));
+    APT_TRY(require_device());
+    const Plan &p = d->plan;
+    d->device = device;
+    APT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    APT_CUDA(cudaGetDeviceProperties(&prop, device));
+    d->sm_count = prop.multiProcessorCount;
+
+    struct Rollback {
+        apt_decoder *d;
+        bool armed = true;
+        ~Rollback() {
+            if (armed) free_decoder_buffers(d);
+        }
+    } rollback{d.get()};
+
+    APT_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    d->max_samples = max_samples;
+    d->max_work = plan_work_len(p, max_samples);
+    d->max_out = plan_out_bound(p, max_samples);
+    if (d->max_work >= (1ull << 32))
+        return fail(APT_ERR_BAD_ARG, "recording too long: %llu work-rate samples (limit 2^32-1)",
+                    (unsigned long long)d->max_work);
+
+    const float one = 1.f;
+    APT_CUDA(cudaMalloc(&d->d_h, p.h.size() * sizeof(float)));
+    APT_CUDA(cudaMemcpy(d->d_h, p.h.data(), p.h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    APT_CUDA(cudaMalloc(&d->d_lp, p.lp.size() * sizeof(float)));
+    APT_CUDA(cudaMemcpy(d->d_lp, p.lp.data(), p.lp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    APT_CUDA(cudaMalloc(&d->d_one, sizeof(float)));
+    APT_CUDA(cudaMemcpy(d->d_one, &one, sizeof(float), cudaMemcpyHostToDevice));
+    const size_t work_bytes = std::max<uint64_t>(d->max_work, 1) * sizeof(float);
+    if (!p.first_polyphase) APT_CUDA(cudaMalloc(&d->d_r, work_bytes));
+    APT_CUDA(cudaMalloc(&d->d_e, work_bytes));
+    APT_CUDA(cudaMalloc(&d->d_f, work_bytes));
+    APT_TRY(alloc_sync_buffers(d.get()));
+    APT_CUDA(cudaMalloc(&d->d_res, sizeof(SyncResult)));
+    APT_CUDA(cudaMemset(d->d_res, 0, sizeof(SyncResult)));
+    APT_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&d->h_res), sizeof(SyncResult), cudaHostAllocDefault));
+    memset(d->h_res, 0, sizeof(SyncResult));
+    rollback.armed = false;
+    *dec = d.release();
+    return APT_OK;
+}
+
+extern "C" void apt_decoder_destroy(apt_decoder *dec) {
+    if (!dec) return;
+    free_decoder_buffers(dec);
+    delete dec;
+}
+
+namespace {
+
+int submit_common(apt_decoder *d, const void *signal, int format, uint64_t n, int sync, float *out, uint64_t cap,
+                  bool host) {
+    if (!d) return fail(APT_ERR_BAD_ARG, "null decoder");
+    if (d->in_flight) return fail(APT_ERR_BAD_ARG, "decoder already has a job in flight; call apt_decoder_wait first");
+    if (format != APT_F32 && format != APT_PCM16) return fail(APT_ERR_BAD_ARG, "unknown sample format %d", format);
+    if (n == 0 || !signal) return fail(APT_ERR_BAD_ARG, "empty signal");   // signal[0] panics in demodulate, dsp.rs:367
+    if (n > d->max_samples)
+        return fail(APT_ERR_BAD_ARG, "recording of %llu samples exceeds the decoder's max_samples %llu",
+                    (unsigned long long)n, (unsigned long long)d->max_samples);
+    const Plan &p = d->plan;
+    APT_CUDA(cudaSetDevice(d->device));
+
+    d->job_status = APT_OK;
+    d->job_host = host;
+    d->job_sync = sync != 0;
+    d->job_n = n;
+    d->job_out = out;
+    d->job_cap = cap;
+    d->job_fixed_out = 0;
+
+    const uint64_t nwork = plan_work_len(p, n);
+    d->job_work = nwork;
+    if (nwork < 10ull * p.row) {   // decode.rs:79-83
+        d->job_status = fail(APT_ERR_TOO_SHORT, "Got less than 10 rows of samples, audio file is too short");
+        return d->job_status;
+    }
+    const uint64_t need = d->job_sync ? (nwork / p.row) * kPxPerRow : plan_out_bound(p, n);
+    if (!out || cap < need) return fail(APT_ERR_CAPACITY, "output needs room for %llu floats", (unsigned long long)need);
+
+    const void *dev_in = signal;
+    float *rows_dst = out;
+    if (host) {
+        if (!d->d_in) APT_CUDA(cudaMalloc(&d->d_in, std::max<uint64_t>(d->max_samples, 1) * sizeof(float)));
+        if (!d->d_out) APT_CUDA(cudaMalloc(&d->d_out, std::max<uint64_t>(d->max_out, 1) * sizeof(float)));
+        APT_CUDA(cudaMemcpyAsync(d->d_in, signal, n * sample_bytes(format), cudaMemcpyHostToDevice, d->stream));
+        dev_in = d->d_in;
+        rows_dst = d->d_out;
+    }
+    d->job_rows_src = rows_dst;
+    int st = decoder_enqueue(d, dev_in, format, n, sync, rows_dst);
+    if (st != APT_OK) {
+        cudaStreamSynchronize(d->stream);
+        d->job_status = st;
+        return st;
+    }
+    if (d->job_sync)
+        APT_CUDA(cudaMemcpyAsync(d->h_res, d->d_res, sizeof(SyncResult), cudaMemcpyDeviceToHost, d->stream));
+    else if (host && d->job_fixed_out)
+        APT_CUDA(cudaMemcpyAsync(out, d->d_out, d->job_fixed_out * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+    d->in_flight = true;
+    return APT_OK;
+}
+
+}  // namespace
+
+extern "C" int apt_decoder_submit_device(apt_decoder *dec, const void *signal, int format, uint64_t n, int sync,
+                                         float *out, uint64_t cap) {
+    return submit_common(dec, signal, format, n, sync, out, cap, false);
+}
+
+extern "C" int apt_decoder_submit_host(apt_decoder *dec, const void *signal, int format, uint64_t n, int sync,
+                                       float *out, uint64_t cap) {
+    return submit_common(dec, signal, format, n, sync, out, cap, true);
+}
+
+extern "C" int apt_decoder_wait(apt_decoder *d, uint64_t *nout) {
+    if (!d) return fail(APT_ERR_BAD_ARG, "null decoder");
+    if (nout) *nout = 0;
+    if (!d->in_flight) return d->job_status;
+    APT_CUDA(cudaSetDevice(d->device));
+    d->in_flight = false;
+    APT_CUDA(cudaStreamSynchronize(d->stream));
+    uint64_t produced = d->job_fixed_out;
+    d->last_work = d->job_work;
+    d->last_peaks = 0;
+    if (d->job_sync) {
+        const SyncResult res = *d->h_res;
+        d->last_peaks = res.n_peaks;
+        if (res.status != APT_OK) {
+            d->job_status = fail(static_cast<int>(res.status),
+                                 "Found less than 5 sync frames, audio file is too short or too noisy");
+            return d->job_status;
+        }
+        produced = static_cast<uint64_t>(res.n_rows) * kPxPerRow;
+        if (d->job_host && produced) {
+            APT_CUDA(cudaMemcpyAsync(d->job_out, d->d_out, produced * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+            APT_CUDA(cudaStreamSynchronize(d->stream));
+        }
+    }
+    d->last_rows = d->plan.work_multiple ? produced / kPxPerRow : 0;
+    d->last_out = produced;
+    if (d->profiling) {
+        d->kernel_ms.assign(d->ev_used, 0.f);
+        for (int i = 0; i < d->ev_used; ++i) cudaEventElapsedTime(&d->kernel_ms[i], d->ev_begin[i], d->ev_end[i]);
+    }
+    if (nout) *nout = produced;
+    return APT_OK;
+}
+
+extern "C" int apt_decoder_last_sync(apt_decoder *d, uint64_t *positions, size_t cap, size_t *npositions) {
+    if (!d || !npositions) return fail(APT_ERR_BAD_ARG, "null argument");
+    APT_CUDA(cudaSetDevice(d->device));
+    const size_t got = d->last_peaks;
+    *npositions = got;
+    if (positions && got) {
+        std::vector<u32> tmp(got);
+        APT_CUDA(cudaMemcpy(tmp.data(), d->d_pos, got * sizeof(u32), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < std::min(got, cap); ++i) positions[i] = tmp[i];
+    }
+    return APT_OK;
+}
+
+extern "C" int apt_decoder_last_counts(apt_decoder *d, uint64_t *n_work, uint64_t *n_rows, uint64_t *n_peaks) {
+    if (!d) return fail(APT_ERR_BAD_ARG, "null decoder");
+    if (n_work) *n_work = d->last_work;
+    if (n_rows) *n_rows = d->last_rows;
+    if (n_peaks) *n_peaks = d->last_peaks;
+    return APT_OK;
+}
+
+extern "C" int apt_decoder_read_stage(apt_decoder *d, int which, float *out, uint64_t cap, uint64_t *n) {
+    if (!d || !n) return fail(APT_ERR_BAD_ARG, "null argument");
+    APT_CUDA(cudaSetDevice(d->device));
+    const float *src = nullptr;
+    uint64_t len = d->last_work;
+    switch (which) {
+    case 0: src = d->d_e; break;
+    case 1: src = d->d_f; break;
+    case 2:
+        src = d->d_corr;
+        len = d->last_work > d->plan.guard.size() ? d->last_work - d->plan.guard.size() : 0;
+        break;
+    default: return fail(APT_ERR_BAD_ARG, "unknown stage %d", which);
+    }
+    if (!src) len = 0;
+    *n = len;
+    if (out && len) {
+        if (cap < len) return fail(APT_ERR_CAPACITY, "stage needs %llu floats", (unsigned long long)len);
+        APT_CUDA(cudaMemcpy(out, src, len * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return APT_OK;
+}
+
+extern "C" int apt_decoder_set_profiling(apt_decoder *d, int enabled) {
+    if (!d) return fail(APT_ERR_BAD_ARG, "null decoder");
+    d->profiling = enabled != 0;
+    return APT_OK;
+}
+
+extern "C" int apt_decoder_kernel_count(apt_decoder *d) { return d ? static_cast<int>(d->kernel_ms.size()) : 0; }
+
+extern "C" const char *apt_decoder_kernel_name(apt_decoder *d, int i) {
+    if (!d || i < 0 || i >= static_cast<int>(d->kernel_names.size())) return "";
+    return d->kernel_names[i].c_str();
+}
+
+extern "C" int apt_decoder_kernel_ms(apt_decoder *d, float *ms, int cap, int *count) {
+    if (!d || !count) return fail(APT_ERR_BAD_ARG, "null argument");
+    *count = static_cast<int>(d->kernel_ms.size());
+    for (int i = 0; i < std::min(cap, *count); ++i) ms[i] = d->kernel_ms[i];
+    return APT_OK;
+}
+
+extern "C" void *apt_decoder_stream(apt_decoder *d) { return d ? static_cast<void *>(d->stream) : nullptr; }
+extern "C" uint64_t apt_decoder_launch_count(apt_decoder *d) { return d ? d->launches : 0; }
+
+// ============================================================================ memory helpers
+
+extern "C" int apt_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return fail(APT_ERR_BAD_ARG, "null argument");
+    APT_TRY(require_device());
+    APT_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 4, cudaHostAllocPortable));
+    return APT_OK;
+}
+
+extern "C" void apt_host_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+extern "C" int apt_device_alloc(int device, void **ptr, size_t bytes) {
+    if (!ptr) return fail(APT_ERR_BAD_ARG, "null argument");
+    APT_TRY(require_device());
+    APT_CUDA(cudaSetDevice(device));
+    APT_CUDA(cudaMalloc(ptr, bytes ? bytes : 4));
+    return APT_OK;
+}
+
+extern "C" void apt_device_free(int device, void *ptr) {
+    if (!ptr) return;
+    cudaSetDevice(device);
+    cudaFree(ptr);
+}
+
+extern "C" int apt_memcpy_h2d(int device, void *dst, const void *src, size_t bytes) {
+    APT_CUDA(cudaSetDevice(device));
+    APT_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return APT_OK;
+}
+
+extern "C" int apt_memcpy_d2h(int device, void *dst, const void *src, size_t bytes) {
+    APT_CUDA(cudaSetDevice(device));
+    APT_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return APT_OK;
+}
+
+// ============================================================================ one-shot decode
+
+namespace {
+
+int decode_oneshot(const void *signal, int format, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
+                   float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user) {
+    if (!s || !nout) return fail(APT_ERR_BAD_ARG, "null argument");
+    *nout = 0;
+    if (n == 0 || !signal) return fail(APT_ERR_BAD_ARG, "empty signal");
+    int device = 0;
+    apt_decoder *d = nullptr;
+    {
+        // errors that do not need a device come first, in the reference's order
+        Plan p;
+        APT_TRY(make_plan(input_rate, *s, p));
+        if (plan_work_len(p, n) < 10ull * p.row)
+            return fail(APT_ERR_TOO_SHORT, "Got less than 10 rows of samples, audio file is too short");
+        if (sync && !p.work_multiple) return fail(APT_ERR_WORK_RATE, "work_rate is not multiple of FINAL_RATE");
+    }
+    APT_TRY(require_device());
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    APT_TRY(apt_decoder_create(device, input_rate, s, n, &d));
+    d->cb = cb;
+    d->cb_user = user;
+    int st = apt_decoder_submit_host(d, signal, format, n, sync, out, cap);
+    if (st == APT_OK) st = apt_decoder_wait(d, nout);
+    apt_decoder_destroy(d);
+    return st;
+}
+
+}  // namespace
+
+extern "C" int apt_decode(const float *signal, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
+                          float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user) {
+    return decode_oneshot(signal, APT_F32, n, input_rate, s, sync, out, cap, nout, cb, user);
+}
+
+extern "C" int apt_decode_pcm16(const int16_t *pcm, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
+                                float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user) {
+    return decode_oneshot(pcm, APT_PCM16, n, input_rate, s, sync, out, cap, nout, cb, user);
+}
+
+// ===================================================================================== batch
+
+extern "C" int apt_decode_batch(const void *const *signals, int format, const uint64_t *lens, int count,
+                                uint32_t input_rate, const apt_settings *s, int sync, float *const *outs,
+                                const uint64_t *caps, uint64_t *nouts, int *statuses, const int *devices, int ndevices,
+                                int streams_per_device) {
+    if (!signals || !lens || !s || !outs || !caps || !nouts || count < 0)
+        return fail(APT_ERR_BAD_ARG, "null argument");
+    if (count == 0) return APT_OK;
+    APT_TRY(require_device());
+    int default_device = 0;
+    if (!devices || ndevices <= 0) {
+        devices = &default_device;
+        ndevices = 1;
+    }
+    if (streams_per_device <= 0) streams_per_device = 4;
+    uint64_t max_len = 0;
+    for (int i = 0; i < count; ++i) max_len = std::max(max_len, lens[i]);
+
+    const int nslots = ndevices * streams_per_device;   // decoders are created lazily
+    std::vector<apt_decoder *> slots(nslots, nullptr);
+    std::vector<int> slot_job(nslots, -1);
+    int first_error = APT_OK;
+    auto finish = [&](int slot) {
+        const int job = slot_job[slot];
+        if (job < 0) return;
+        uint64_t got = 0;
+        int st = apt_decoder_wait(slots[slot], &got);
+        nouts[job] = got;
+        if (statuses) statuses[job] = st;
+        if (st != APT_OK && first_error == APT_OK) first_error = st;
+        slot_job[slot] = -1;
+    };
+    int fatal = APT_OK;
+    for (int i = 0; i < count && fatal == APT_OK; ++i) {
+        // recording i -> device i % G, stream (i / G) % S   
+        const int dev_idx = i % ndevices;
+        const int slot = dev_idx * streams_per_device + (i / ndevices) % streams_per_device;
+        if (!slots[slot]) {
+            fatal = apt_decoder_create(devices[dev_idx], input_rate, s, max_len, &slots[slot]);
+            if (fatal != APT_OK) break;
+        }
+        finish(slot);
+        nouts[i] = 0;
+        int st = apt_decoder_submit_host(slots[slot], signals[i], format, lens[i], sync, outs[i], caps[i]);
+        if (st == APT_OK) {
+            slot_job[slot] = i;
+        } else {
+            if (statuses) statuses[i] = st;
+            if (first_error == APT_OK) first_error = st;
+        }
+    }
+    for (int slot = 0; slot < nslots; ++slot) {
+        if (slots[slot]) {
+            finish(slot);
+            apt_decoder_destroy(slots[slot]);
+        }
+    }
+    return fatal != APT_OK ? fatal : first_error;
+}

@@ -1,0 +1,220 @@
+// Decoder object and kernel sequence of decode::decode (decode.rs:43-162).
+#include "decoder.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.hpp"
+#include "launch.hpp"
+
+namespace aptb200 {
+
+std::string &last_error_slot() {
+    static thread_local std::string slot;
+    return slot;
+}
+
+int fail(int status, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error_slot() = buf;
+    return status;
+}
+
+// ------------------------------------------------------------------------------------- plan
+
+int make_plan(uint32_t input_rate, const apt_settings &s, Plan &p) {
+    p = Plan{};
+    p.input_rate = input_rate;
+    p.st = s;
+    if (s.work_rate > UINT32_MAX / kPxPerRow)   // PX_PER_ROW * work_rate overflows u32 (decode.rs:55)
+        return fail(APT_ERR_BAD_ARG, "work_rate %u is too large", s.work_rate);
+
+    // decode.rs:65-77 -> dsp::resample_with_filter (dsp.rs:62-98)
+    int st = resample_ratio(input_rate, s.work_rate, p.first);
+    if (st == APT_ERR_RESAMPLE_TO_ZERO) return fail(st, "Can't resample to 0Hz");
+    if (st == APT_ERR_RATE_OVERFLOW)
+        return fail(st, "Can't resample, looks like the sample rates do not have a big divisor in common. "
+                        "input_rate: %u, output_rate: %u, l: %u, m: %u",
+                    input_rate, s.work_rate, p.first.l, p.first.m);
+    if (st != APT_OK) return fail(st, "invalid input rate %u", input_rate);
+    p.first_polyphase = p.first.l > 1;
+
+    apt_filter rf{APT_FILTER_LOWPASS_DC, Freq::hz(s.resample_cutout, input_rate).get_pi_rad(), s.resample_atten,
+                  Freq::hz(s.resample_delta_freq, input_rate).get_pi_rad()};
+    if (p.first_polyphase) resample_filter(rf, input_rate, input_rate * p.first.l);   // dsp.rs:93
+    st = design(rf, p.h);
+    if (st != APT_OK) return fail(st, "resampling filter cannot be designed (atten %g, delta_w %g)",
+                                  (double)rf.atten, (double)rf.delta_w_pi);
+    p.off2 = 2 * ((static_cast<uint64_t>(p.h.size()) - 1) / 2);
+
+    // decode.rs:95-100
+    const float cut = static_cast<float>(kFinalRate) / static_cast<float>(s.work_rate);
+    apt_filter lf{APT_FILTER_LOWPASS, cut, s.demodulation_atten, cut / 5.f};
+    st = design(lf, p.lp);
+    if (st != APT_OK) return fail(st, "demodulation filter cannot be designed (atten %g)", (double)lf.atten);
+
+    // decode.rs:89 + dsp.rs:360-363
+    const float phi = 2.f * Freq::hz(static_cast<float>(kCarrierHz), s.work_rate).get_rad();
+    p.cosphi2 = std::cos(phi) * 2.f;
+    p.sinphi = std::sin(phi);
+
+    p.row = kPxPerRow * s.work_rate / kFinalRate;                       // decode.rs:55
+    p.dist = static_cast<uint32_t>(static_cast<uint64_t>(p.row) * 8 / 10);   // decode.rs:216
+    p.work_multiple = s.work_rate % kFinalRate == 0;
+    p.dec = s.work_rate / kFinalRate;
+    if (p.work_multiple) sync_frame(s.work_rate, p.guard);
+    // final stage ratio, decode.rs:158-159 (errors surface when the stage runs)
+    p.last = Ratio{0, 0};
+    resample_ratio(s.work_rate, kFinalRate, p.last);
+    return APT_OK;
+}
+
+uint64_t plan_work_len(const Plan &p, uint64_t n) {
+    if (p.first_polyphase) return polyphase_len(n, p.first.l, p.first.m, p.h.size());
+    return n / p.first.m;   // decimate, dsp.rs:299-301
+}
+
+uint64_t plan_out_bound(const Plan &p, uint64_t n) {
+    const uint64_t nw = plan_work_len(p, n);
+    if (p.row == 0) return 0;
+    const uint64_t rows = nw / p.row;
+    if (p.work_multiple) return rows * kPxPerRow;
+    return polyphase_len(rows * p.row, p.last.l, p.last.m, 1);
+}
+
+// ---------------------------------------------------------------------------------- helpers
+
+namespace {
+
+struct Prof {
+    apt_decoder *d;
+    int slot;
+    Prof(apt_decoder *dec, const char *name) : d(dec), slot(-1) {
+        d->launches++;
+        if (!d->profiling) return;
+        slot = d->ev_used++;
+        if (slot >= static_cast<int>(d->ev_begin.size())) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            d->ev_begin.push_back(a);
+            d->ev_end.push_back(b);
+            d->kernel_names.emplace_back();
+        }
+        d->kernel_names[slot] = name;
+        cudaEventRecord(d->ev_begin[slot], d->stream);
+    }
+    ~Prof() {
+        if (slot >= 0) cudaEventRecord(d->ev_end[slot], d->stream);
+    }
+};
+
+}  // namespace
+
+// Cross-correlation + roots + orbit walk: decode::find_sync (decode.rs:204-263) on d_f[0..nwork).
+int run_find_sync(apt_decoder *d, uint64_t nwork) {
+    const Plan &p = d->plan;
+    const LaunchCtx c{d->stream, d->sm_count};
+    const uint32_t glen = static_cast<uint32_t>(p.guard.size());
+    const uint64_t ncorr = nwork - glen;
+    const uint32_t nblocks = static_cast<uint32_t>((ncorr + p.dist - 1) / p.dist);
+    {
+        Prof pr(d, "sync_correlation");
+        APT_TRY(launch_corr(c, d->d_f, ncorr, d->d_guard, glen, d->d_corr));
+    }
+    {
+        Prof pr(d, "sync_roots");
+        APT_TRY(launch_roots(c, d->d_corr, ncorr, p.dist, d->d_root_list, d->d_root_count, d->d_res));
+    }
+    {
+        Prof pr(d, "sync_pick");
+        APT_TRY(launch_pick(c, ncorr, nwork, p.row, p.dist, d->d_root_list, d->d_root_count, nblocks, d->d_pos,
+                            d->max_positions, d->d_res));
+    }
+    return APT_OK;
+}
+
+static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n, uint64_t nwork) {
+    const Plan &p = d->plan;
+    const LaunchCtx c{d->stream, d->sm_count};
+    if (d->cb) {
+        char msg[64];
+        snprintf(msg, sizeof(msg), "Resampling to %u", p.st.work_rate);
+        d->cb(0.1f, msg, d->cb_user);                                       // decode.rs:63
+    }
+    if (p.first_polyphase) {
+        // fast_resampling + demodulate fused: r is never written (decode.rs:77,89)
+        Prof pr(d, "resample_envelope");
+        APT_TRY(launch_polyphase(c, in, format, n, d->d_h, p.first.l, p.first.m, p.off2, nwork, true, p.cosphi2,
+                                 p.sinphi, d->d_e));
+        if (d->cb) d->cb(0.4f, "Demodulating", d->cb_user);                 // decode.rs:87
+    } else {
+        {
+            Prof pr(d, "filter_decimate");
+            APT_TRY(launch_fir_decimate(c, in, format, d->d_h, static_cast<u32>(p.h.size()), p.first.m, nwork, d->d_r));
+        }
+        if (d->cb) d->cb(0.4f, "Demodulating", d->cb_user);
+        Prof pr(d, "envelope");
+        APT_TRY(launch_envelope(c, d->d_r, nwork, p.cosphi2, p.sinphi, d->d_e));
+    }
+    if (d->cb) d->cb(0.42f, "Filtering", d->cb_user);                       // decode.rs:93
+    {
+        Prof pr(d, "lowpass");
+        APT_TRY(launch_fir_decimate(c, d->d_e, APT_F32, d->d_lp, static_cast<u32>(p.lp.size()), 1, nwork, d->d_f));
+    }
+    return APT_OK;
+}
+
+// Enqueues the whole of decode() on the decoder's stream.  `in` and `rows_out` are device pointers.
+int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int sync, float *rows_out) {
+    const Plan &p = d->plan;
+    const LaunchCtx c{d->stream, d->sm_count};
+    const uint64_t nwork = plan_work_len(p, n);
+    d->job_work = nwork;
+    d->ev_used = 0;
+
+    APT_TRY(enqueue_front(d, in, format, n, nwork));
+
+    if (sync) {
+        if (d->cb) d->cb(0.5f, "Syncing", d->cb_user);                      // decode.rs:107
+        if (!p.work_multiple)
+            return fail(APT_ERR_WORK_RATE, "work_rate is not multiple of FINAL_RATE");   // decode.rs:172-176
+        APT_TRY(run_find_sync(d, nwork));
+        if (d->cb) d->cb(0.9f, "Resampling to 4160", d->cb_user);           // decode.rs:154
+        Prof pr(d, "gather_rows");
+        const u32 max_rows = static_cast<u32>(std::min<uint64_t>(nwork / p.row + 1, 1u << 30));
+        APT_TRY(launch_gather(c, d->d_f, d->d_pos, d->d_res, 0, max_rows, p.row, kPxPerRow, p.dec, rows_out));
+        d->job_fixed_out = 0;
+        return APT_OK;
+    }
+
+    if (d->cb) d->cb(0.5f, "Skipping Syncing", d->cb_user);                 // decode.rs:136
+    const uint64_t rows = nwork / p.row;                                    // decode.rs:141-147
+    if (d->cb) d->cb(0.9f, "Resampling to 4160", d->cb_user);
+    if (p.work_multiple) {
+        Prof pr(d, "gather_rows");
+        APT_TRY(launch_gather(c, d->d_f, nullptr, d->d_res, static_cast<u32>(rows), static_cast<u32>(rows), p.row,
+                              kPxPerRow, p.dec, rows_out));
+        d->job_fixed_out = rows * kPxPerRow;
+        return APT_OK;
+    }
+    // work_rate is not a multiple of 4160: the final stage is a real L/M resample with the one-tap
+    // NoFilter (dsp.rs:79-98), i.e. zero-stuffing then keeping every M-th sample.
+    if (p.last.l == 0) return fail(APT_ERR_RESAMPLE_TO_ZERO, "Can't resample to 0Hz");
+    if (static_cast<uint64_t>(p.st.work_rate) * p.last.l > UINT32_MAX)
+        return fail(APT_ERR_RATE_OVERFLOW, "Can't resample, looks like the sample rates do not have a big divisor "
+                                           "in common. input_rate: %u, output_rate: %u", p.st.work_rate, kFinalRate);
+    const uint64_t alen = rows * p.row;
+    const uint64_t nout = polyphase_len(alen, p.last.l, p.last.m, 1);
+    Prof pr(d, "final_resample");
+    APT_TRY(launch_polyphase(c, d->d_f, APT_F32, alen, d->d_one, p.last.l, p.last.m, 0, nout, false, 0.f, 1.f, rows_out));
+    d->job_fixed_out = nout;
+    return APT_OK;
+}
+
+}  // namespace aptb200

@@ -1,0 +1,90 @@
+// The decoder object behind the C ABI: plan (filters, rates, sizes), device workspaces, one
+// stream, and the kernel sequence of decode::decode (decode.rs:43-162).
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "aptb200.h"
+#include "filters_host.hpp"
+#include "launch.hpp"
+
+namespace aptb200 {
+
+// decode.rs:14-38
+constexpr uint32_t kFinalRate = 4160;
+constexpr uint32_t kPxPerRow = 2080;
+constexpr uint32_t kCarrierHz = 2400;
+
+// Everything decode() derives from (input_rate, settings) before touching a sample.
+struct Plan {
+    uint32_t input_rate = 0;
+    apt_settings st{};
+    Ratio first{};                 // input_rate -> work_rate (dsp.rs:73-75)
+    bool first_polyphase = false;  // L > 1: fast_resampling; else filter + decimate
+    std::vector<float> h;          // resampling filter taps (LowpassDcRemoval, decode.rs:65-76)
+    uint64_t off2 = 0;             // 2 * ((N-1)/2): highest tap index fast_resampling touches
+    std::vector<float> lp;         // demodulation low-pass taps (Lowpass, decode.rs:95-100)
+    float cosphi2 = 0.f, sinphi = 1.f;   // dsp.rs:360-363
+    uint32_t row = 0;              // samples_per_work_row (decode.rs:55)
+    uint32_t dist = 0;             // min_distance (decode.rs:216)
+    bool work_multiple = false;    // work_rate % 4160 == 0
+    uint32_t dec = 0;              // work_rate / 4160 when work_multiple
+    Ratio last{};                  // work_rate -> 4160 for the final NoFilter resample
+    std::vector<int8_t> guard;     // sync template (empty unless work_multiple)
+};
+
+int make_plan(uint32_t input_rate, const apt_settings &s, Plan &plan);
+// N_w for n input samples.
+uint64_t plan_work_len(const Plan &p, uint64_t n);
+// decode() output length for no-sync / upper bound for sync.
+uint64_t plan_out_bound(const Plan &p, uint64_t n);
+
+}  // namespace aptb200
+
+struct apt_decoder {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    aptb200::Plan plan;
+
+    uint64_t max_samples = 0, max_work = 0, max_corr = 0, max_out = 0;
+    uint32_t max_blocks = 0, max_positions = 0;
+
+    float *d_h = nullptr, *d_lp = nullptr, *d_one = nullptr;
+    int8_t *d_guard = nullptr;
+    void *d_in = nullptr;          // staging for submit_host (f32 sized)
+    float *d_r = nullptr;          // resampled signal, only for the L == 1 first stage
+    float *d_e = nullptr;          // envelope           ("demodulation_result")
+    float *d_f = nullptr;          // low-passed         ("filter_result")
+    float *d_corr = nullptr;       // sync correlation   ("sync_correlation")
+    float *d_aligned = nullptr;    // only when work_rate is not a multiple of 4160 (no-sync)
+    aptb200::u32 *d_root_list = nullptr, *d_root_count = nullptr, *d_pos = nullptr;
+    aptb200::SyncResult *d_res = nullptr;
+    float *d_out = nullptr;        // rows for submit_host
+    aptb200::SyncResult *h_res = nullptr;   // pinned
+
+    // job in flight
+    bool in_flight = false;
+    bool job_host = false, job_sync = false;
+    int job_status = APT_OK;
+    uint64_t job_n = 0, job_work = 0, job_corr = 0, job_fixed_out = 0;
+    float *job_out = nullptr;      // caller's buffer (host or device)
+    uint64_t job_cap = 0;
+    const float *job_rows_src = nullptr;
+    uint64_t last_work = 0, last_rows = 0, last_peaks = 0, last_out = 0;
+
+    // profiling
+    bool profiling = false;
+    std::vector<std::string> kernel_names;
+    std::vector<cudaEvent_t> ev_begin, ev_end;
+    std::vector<float> kernel_ms;
+    int ev_used = 0;
+    uint64_t launches = 0;
+
+    apt_status_cb cb = nullptr;
+    void *cb_user = nullptr;
+};

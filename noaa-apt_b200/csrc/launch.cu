@@ -1,0 +1,105 @@
+// Kernel launchers: the only translation unit that instantiates the kernels.
+#include "launch.hpp"
+
+#include <algorithm>
+
+#include "aptb200.h"
+#include "common.hpp"
+#include "kernels_generic.cuh"
+#include "kernels_sync.cuh"
+
+namespace aptb200 {
+
+namespace {
+
+inline unsigned grid_for(u64 n, unsigned per_block, int sms) {
+    const u64 blocks = (n + per_block - 1) / per_block;
+    const u64 cap = static_cast<u64>(sms) * 16;
+    return static_cast<unsigned>(std::max<u64>(1, std::min(blocks, cap)));
+}
+
+template <int CHUNK>
+int roots_with_chunk(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32 nblocks, u32 *root_list,
+                     u32 *root_count, SyncResult *result) {
+    const size_t smem = 2ull * dist * sizeof(float);
+    auto kern = k_roots<1024, CHUNK>;
+    APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<nblocks, 1024, smem, c.stream>>>(corr, ncorr, dist, root_list, root_count, result);
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+}  // namespace
+
+int launch_polyphase(const LaunchCtx &c, const void *signal, int format, u64 len, const float *taps, u32 l, u32 m,
+                     u64 off2, u64 nout, bool envelope, float cosphi2, float sinphi, float *out) {
+    if (nout == 0) return APT_OK;
+    const unsigned grid = grid_for(nout, 256, c.sm_count);
+    if (format == APT_PCM16) {
+        const int16_t *s = static_cast<const int16_t *>(signal);
+        if (envelope) k_polyphase_generic<int16_t, true><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, nout, cosphi2, sinphi, out);
+        else k_polyphase_generic<int16_t, false><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, nout, cosphi2, sinphi, out);
+    } else {
+        const float *s = static_cast<const float *>(signal);
+        if (envelope) k_polyphase_generic<float, true><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, nout, cosphi2, sinphi, out);
+        else k_polyphase_generic<float, false><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, nout, cosphi2, sinphi, out);
+    }
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+int launch_fir_decimate(const LaunchCtx &c, const void *signal, int format, const float *coeff, u32 ntaps, u32 m,
+                        u64 nout, float *out) {
+    if (nout == 0) return APT_OK;
+    const unsigned grid = grid_for(nout, 256, c.sm_count);
+    if (format == APT_PCM16)
+        k_fir_decimate_generic<int16_t><<<grid, 256, 0, c.stream>>>(static_cast<const int16_t *>(signal), coeff, ntaps, m, nout, out);
+    else
+        k_fir_decimate_generic<float><<<grid, 256, 0, c.stream>>>(static_cast<const float *>(signal), coeff, ntaps, m, nout, out);
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+int launch_envelope(const LaunchCtx &c, const float *x, u64 n, float cosphi2, float sinphi, float *out) {
+    if (n == 0) return APT_OK;
+    k_envelope<<<grid_for(n, 256, c.sm_count), 256, 0, c.stream>>>(x, n, cosphi2, sinphi, out);
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+int launch_corr(const LaunchCtx &c, const float *f, u64 ncorr, const int8_t *guard, u32 glen, float *corr) {
+    if (ncorr == 0) return APT_OK;
+    k_corr_generic<<<grid_for(ncorr, 256, c.sm_count), 256, 0, c.stream>>>(f, ncorr, guard, glen, corr);
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32 *root_list, u32 *root_count,
+                 SyncResult *result) {
+    const u32 nblocks = static_cast<u32>((ncorr + dist - 1) / dist);
+    const u32 need = (dist + 1023) / 1024;
+    if (need <= 5) return roots_with_chunk<5>(c, corr, ncorr, dist, nblocks, root_list, root_count, result);
+    if (need <= 7) return roots_with_chunk<7>(c, corr, ncorr, dist, nblocks, root_list, root_count, result);
+    if (need <= 9) return roots_with_chunk<9>(c, corr, ncorr, dist, nblocks, root_list, root_count, result);
+    if (need <= 16) return roots_with_chunk<16>(c, corr, ncorr, dist, nblocks, root_list, root_count, result);
+    return fail(APT_ERR_BAD_ARG, "work rate too high for the sync picker (min_distance %u)", dist);
+}
+
+int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *root_list,
+                const u32 *root_count, u32 nblocks, u32 *positions, u32 max_positions, SyncResult *result) {
+    k_pick_sequential<<<1, 32, 0, c.stream>>>(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions,
+                                              max_positions, result);
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+int launch_gather(const LaunchCtx &c, const float *f, const u32 *positions, const SyncResult *result,
+                  u32 fixed_rows, u32 max_rows, u32 row, u32 px, u32 dec, float *out) {
+    if (max_rows == 0) return APT_OK;
+    const unsigned grid = std::min<unsigned>(max_rows, static_cast<unsigned>(c.sm_count) * 16);
+    k_gather_rows<<<grid, 256, 0, c.stream>>>(f, positions, result, fixed_rows, row, px, dec, out);
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+}  // namespace aptb200

@@ -1,0 +1,51 @@
+// Host-callable launchers of every kernel of the decode path (defined in launch.cu, the only
+// translation unit that sees the kernels).  All pointers are device pointers.
+#pragma once
+
+#include <cstdint>
+
+#include <cuda_runtime.h>
+
+namespace aptb200 {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// Device-side summary of one decode (read back by the host after the stream drains).
+struct SyncResult {
+    u32 n_peaks;       // sync_pos.len()                       (decode.rs:110)
+    u32 n_rows;        // rows that pass `pos + row < len`     (decode.rs:127)
+    u32 status;        // APT_OK or APT_ERR_FEW_SYNC_FRAMES    (decode.rs:112-118)
+    u32 seed_index;    // first i in [0, D] with corr[i] > 0, or 0xFFFFFFFF
+    u32 n_roots;       // total number of roots (diagnostic)
+    u32 pad[3];
+};
+
+
+struct LaunchCtx {
+    cudaStream_t stream;
+    int sm_count;
+};
+
+// fast_resampling (dsp.rs:186-289), optionally fused with demodulate (dsp.rs:350-383).
+// format: APT_F32 / APT_PCM16 samples.
+int launch_polyphase(const LaunchCtx &c, const void *signal, int format, u64 len, const float *taps, u32 l, u32 m,
+                     u64 off2, u64 nout, bool envelope, float cosphi2, float sinphi, float *out);
+// dsp::filter + decimate (dsp.rs:396-404, 299-303).
+int launch_fir_decimate(const LaunchCtx &c, const void *signal, int format, const float *coeff, u32 ntaps, u32 m,
+                        u64 nout, float *out);
+// dsp::demodulate (dsp.rs:350-383).
+int launch_envelope(const LaunchCtx &c, const float *x, u64 n, float cosphi2, float sinphi, float *out);
+// sync cross-correlation (decode.rs:225-233).
+int launch_corr(const LaunchCtx &c, const float *f, u64 ncorr, const int8_t *guard, u32 glen, float *corr);
+// roots of the correlation (see kernels_sync.cuh).
+int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32 *root_list, u32 *root_count,
+                 SyncResult *result);
+// orbit walk -> sync positions (decode.rs:241-253).
+int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *root_list,
+                const u32 *root_count, u32 nblocks, u32 *positions, u32 max_positions, SyncResult *result);
+// aligned rows + final decimation (decode.rs:122-134, 158-159).  positions == nullptr: no-sync rows.
+int launch_gather(const LaunchCtx &c, const float *f, const u32 *positions, const SyncResult *result,
+                  u32 fixed_rows, u32 max_rows, u32 row, u32 px, u32 dec, float *out);
+
+}  // namespace aptb200

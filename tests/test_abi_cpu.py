@@ -1,0 +1,141 @@
+"""CPU-only checks of the drop-in boundary: libaptb200.so loads without a GPU, exports every symbol
+include/aptb200.h declares, and its host-side logic (filter design, unit arithmetic, length and error
+rules) agrees with the oracle.  No kernel runs here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def na():
+    entry.build()
+    import noaa_apt_b200
+    return noaa_apt_b200
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "aptb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set(re.findall(r"\b(apt_[a-z0-9_]+)\s*\(", text))
+    names.discard("apt_status_cb")
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol(na):
+    lib = C.CDLL(na.library_path())
+    names = declared_functions()
+    assert len(names) >= 40
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in aptb200.h but not exported"
+        assert name in na._lib.SIGNATURES, f"{name} has no ctypes prototype"
+    assert set(na._lib.SIGNATURES) == set(names)
+    assert lib.apt_abi_version() == 1
+
+
+def test_filter_taps_bit_identical_to_oracle(na):
+    import oracle
+    for rate, l in ((11025, 832), (48000, 13), (96000, 13), (44100, 208)):
+        f = na.filters.LowpassDcRemoval(na.Freq.hz(4800, rate), 30.0, na.Freq.hz(1000, rate))
+        f.resample(rate, rate * l)
+        ratio = np.float32(rate * l) / np.float32(rate)
+        ref = oracle.design(oracle.FILTER_LOWPASS_DC, np.float32(oracle.freq_hz(4800, rate)) / ratio, 30.0,
+                            np.float32(oracle.freq_hz(1000, rate)) / ratio)
+        got = f.design()
+        assert got.size == ref.size
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert [14057, 959, 1915][1] == 959
+    cut = np.float32(4160) / np.float32(12480)
+    lp = na.filters.Lowpass(na.Freq.pi_rad(cut), 25.0, na.Freq.pi_rad(cut) / 5.0).design()
+    assert lp.size == 37
+    assert np.array_equal(lp, oracle.design(oracle.FILTER_LOWPASS, cut, 25.0, cut / np.float32(5)))
+    assert na.filters.NoFilter().design().tolist() == [1.0]
+
+
+def test_tap_counts_match_survey_appendix_b(na):
+    # 14057 / 959 / 1915 taps for the standard profile
+    for rate, l, n in ((11025, 832, 14057), (48000, 13, 959), (96000, 13, 1915)):
+        f = na.filters.LowpassDcRemoval(na.Freq.hz(4800, rate), 30.0, na.Freq.hz(1000, rate))
+        f.resample(rate, rate * l)
+        assert f.design().size == n
+
+
+def test_filter_resample_equivalence(na):
+    # filters.rs:377-413
+    f = na.filters.Lowpass(na.Freq.hz(123.0, 1000), 40.0, na.Freq.hz(12.0, 1000))
+    f.resample(na.Rate.hz(1000), na.Rate.hz(3000))
+    assert f == na.filters.Lowpass(na.Freq.hz(123.0, 3000), 40.0, na.Freq.hz(12.0, 3000))
+    g = na.filters.NoFilter()
+    g.resample(1000, 3000)
+    assert g == na.filters.NoFilter()
+
+
+def test_bessel_and_sync_frame(na):
+    import oracle
+    lib = na._lib.load()
+    for x in np.linspace(0, 7, 15):
+        assert lib.apt_bessel_i0(float(x)) == oracle.bessel_i0(float(x))
+    for wr in (4160 * 2, 4160 * 3, 4160 * 5):
+        assert np.array_equal(na.generate_sync_frame(wr), oracle.generate_sync_frame(wr))
+    with pytest.raises(na.err.Internal) as e:
+        na.generate_sync_frame(11025)
+    assert e.value.code == na._lib.ERR_WORK_RATE
+
+
+def test_lengths_and_errors_without_a_gpu(na):
+    import oracle
+    lib = na._lib.load()
+    # exact output length of resample_with_filter (polyphase and L == 1)
+    rng = np.random.default_rng(0)
+    for in_rate, out_rate, n in ((11025, 12480, 5000), (48000, 12480, 9000), (24960, 12480, 7001), (1000, 1500, 100)):
+        cf = na.filters.Lowpass(na.Freq.pi_rad(0.2), 30.0, na.Freq.pi_rad(0.05)).to_c()
+        got = C.c_uint64(0)
+        assert lib.apt_resample_len(n, in_rate, out_rate, C.byref(cf), C.byref(got)) == 0
+        ref = oracle.resample_with_filter(rng.standard_normal(n).astype(np.float32), in_rate, out_rate,
+                                          oracle.FILTER_LOWPASS, 0.2, 30.0, 0.05)
+        assert got.value == ref.size
+    # dsp.rs:420-434: RateOverflow for two prime rates
+    cf = na.filters.NoFilter().to_c()
+    got = C.c_uint64(0)
+    assert lib.apt_resample_len(1000, 99371, 93911, C.byref(cf), C.byref(got)) == na._lib.ERR_RATE_OVERFLOW
+    assert b"divisor" in lib.apt_last_error()
+    # dsp.rs:69-71
+    assert lib.apt_resample_len(1000, 11025, 0, C.byref(cf), C.byref(got)) == na._lib.ERR_RESAMPLE_TO_ZERO
+    # decode.rs:79-83 is decided from lengths alone, before any device work
+    with pytest.raises(na.err.Internal) as e:
+        na.decode(na.Context(), na.Settings(), np.zeros(20000, np.float32), 11025, True)
+    assert e.value.code == na._lib.ERR_TOO_SHORT
+    with pytest.raises(na.err.RateOverflow):
+        na.decode(na.Context(), na.Settings(work_rate=93911), np.zeros(200000, np.float32), 99371, True)
+    with pytest.raises(na.err.InvalidInput):
+        na.decode(na.Context(), na.Settings(), np.zeros(0, np.float32), 11025, True)
+    # bound = rows * 2080
+    assert na.decode_len_bound(9_067_017, 11025) == (10_263_607 // 6240) * 2080
+
+
+def test_compute_fails_loudly_without_a_device(na):
+    if na.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from noaa_apt_b200 import synth
+    x = synth.apt_signal(11025, 8, seed=1)
+    with pytest.raises(na.err.CudaError) as e:
+        na.decode(na.Context(), na.Settings(), x, 11025, True)
+    assert "no CPU fallback" in str(e.value)
+    with pytest.raises(na.err.CudaError):
+        na.dsp.demodulate(na.Context(), x[:100], na.Freq.hz(2400, 12480))
+    with pytest.raises(na.err.CudaError):
+        na.Decoder(11025, na.Settings(), max_samples=x.size)
+
+
+def test_profiles(na):
+    s = na.Settings.profile("fast")
+    assert (s.work_rate, s.resample_delta_freq, s.demodulation_atten) == (16640, 3000.0, 23.0)
+    s = na.Settings.profile("slow")
+    assert (s.work_rate, s.resample_atten, s.resample_delta_freq) == (20800, 40.0, 500.0)
+    assert na.Settings.profile("standard") == na.Settings()
