@@ -1,6 +1,7 @@
 // C ABI (include/aptb200.h) over the decoder object and the stage kernels.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -52,7 +53,7 @@ int free_decoder_buffers(apt_decoder *d) {
     if (d->stream) cudaStreamSynchronize(d->stream);
     for (void *p : {(void *)d->d_h, (void *)d->d_lp, (void *)d->d_one, (void *)d->d_guard, d->d_in, (void *)d->d_r,
                     (void *)d->d_e, (void *)d->d_f, (void *)d->d_corr, (void *)d->d_aligned, (void *)d->d_root_list,
-                    (void *)d->d_root_count, (void *)d->d_pos, (void *)d->d_res, (void *)d->d_out})
+                    (void *)d->d_root_count, (void *)d->d_pos, (void *)d->d_res, (void *)d->d_out, d->d_pick})
         if (p) cudaFree(p);
     if (d->h_res) cudaFreeHost(d->h_res);
     for (auto e : d->ev_begin) cudaEventDestroy(e);
@@ -74,6 +75,12 @@ int alloc_sync_buffers(apt_decoder *d) {
     APT_CUDA(cudaMalloc(&d->d_root_list, static_cast<size_t>(d->max_blocks) * p.dist * sizeof(u32)));
     APT_CUDA(cudaMalloc(&d->d_root_count, static_cast<size_t>(d->max_blocks) * sizeof(u32)));
     APT_CUDA(cudaMalloc(&d->d_pos, static_cast<size_t>(d->max_positions) * sizeof(u32)));
+    // parallel picker: room for every row-aligned start plus ~16 roots per row (typical recordings have
+    // ~8); beyond that the kernel falls back to the sequential walk by itself.
+    const u32 cap = static_cast<u32>(std::min<uint64_t>(static_cast<uint64_t>(d->max_positions) * 17 + 65536, 1u << 28));
+    APT_CUDA(cudaMalloc(&d->d_pick, pick_scratch_bytes(d->max_blocks, d->max_positions, cap)));
+    d->pick = pick_scratch_carve(d->d_pick, d->max_blocks, d->max_positions, cap);
+    if (getenv("APTB200_SEQUENTIAL_PICK")) d->use_parallel_pick = false;
     return APT_OK;
 }
 

@@ -134,7 +134,7 @@ int run_find_sync(apt_decoder *d, uint64_t nwork) {
     {
         Prof pr(d, "sync_pick");
         APT_TRY(launch_pick(c, ncorr, nwork, p.row, p.dist, d->d_root_list, d->d_root_count, nblocks, d->d_pos,
-                            d->max_positions, d->d_res));
+                            d->max_positions, d->d_res, d->use_parallel_pick && d->d_pick ? &d->pick : nullptr));
     }
     return APT_OK;
 }

@@ -64,6 +64,9 @@ struct apt_decoder {
     float *d_aligned = nullptr;    // only when work_rate is not a multiple of 4160 (no-sync)
     aptb200::u32 *d_root_list = nullptr, *d_root_count = nullptr, *d_pos = nullptr;
     aptb200::SyncResult *d_res = nullptr;
+    void *d_pick = nullptr;        // scratch of the parallel picker
+    aptb200::PickScratch pick{};
+    bool use_parallel_pick = true;
     float *d_out = nullptr;        // rows for submit_host
     aptb200::SyncResult *h_res = nullptr;   // pinned
 

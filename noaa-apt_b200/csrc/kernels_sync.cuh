@@ -147,13 +147,12 @@ __device__ __forceinline__ u32 first_root(u32 s, u32 dist, const u32 *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_pick_sequential: one thread walks the orbit of F.  O(rows * log) dependent loads -- the
-// always-correct fallback (and the path for pathological inputs with millions of roots).
+// Sequential orbit walk by one thread: O(rows * log) dependent loads.  The always-correct
+// fallback (pathological inputs with millions of roots, e.g. silence) and the v0 picker.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_pick_sequential(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ root_list,
-                                  const u32 *__restrict__ root_count, u32 nblocks, u32 *__restrict__ positions,
-                                  u32 max_positions, SyncResult *__restrict__ result) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+__device__ void pick_sequential(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ root_list,
+                                const u32 *__restrict__ root_count, u32 nblocks, u32 *__restrict__ positions,
+                                u32 max_positions, SyncResult *__restrict__ result) {
     u32 len = 1;
     // peak #1: the seed (0, 0.0), refined if some corr[i] > 0 turns up within D of position 0
     const u32 seed = result->seed_index;
@@ -177,9 +176,222 @@ __global__ void k_pick_sequential(u64 ncorr, u64 nwork, u32 row, u32 dist, const
     result->n_peaks = len;
     result->n_rows = rows;
     result->status = len < 5 ? 3u /* APT_ERR_FEW_SYNC_FRAMES */ : 0u;
+}
+
+__global__ void k_pick_sequential(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ root_list,
+                                  const u32 *__restrict__ root_count, u32 nblocks, u32 *__restrict__ positions,
+                                  u32 max_positions, SyncResult *__restrict__ result) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    pick_sequential(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions, max_positions, result);
     u32 total = 0;
     for (u32 b = 0; b < nblocks; ++b) total += root_count[b];
     result->n_roots = total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_pick_parallel: the orbit of F by pointer doubling, one CTA of 1024 threads.
+//
+// Candidate starts: A_m = row*m (m < NR) and B_r = root_r + D + 1 (one per root) -- F maps every
+// start onto one of these, so F is a table J0 over NR + nroots nodes (+ END).  Level k holds
+// J_k = F^(2^k); the orbit is grown by  orbit[n + 2^k] = J_k[orbit[n]]  for n < 2^k, so only the
+// current level is needed.  All tables live in global scratch (L2-resident, a few hundred KB).
+// Falls back to the sequential walk when the candidate count exceeds the scratch capacity.
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ u32 block_scan_inclusive_1024(u32 v, u32 *s_tmp) {
+    // inclusive scan of one value per thread over a 1024-thread CTA
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) s_tmp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = s_tmp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        s_tmp[lane] = w;
+    }
+    __syncthreads();
+    if (warp > 0) v += s_tmp[warp - 1];
+    __syncthreads();
+    return v;
+}
+
+__global__ void __launch_bounds__(1024)
+k_pick_parallel(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ root_list,
+                const u32 *__restrict__ root_count, u32 nblocks, u32 *__restrict__ positions, u32 max_positions,
+                SyncResult *__restrict__ result, PickScratch sc) {
+    __shared__ u32 s_tmp[32];
+    __shared__ u32 s_misc[4];
+    const u32 tid = threadIdx.x;
+    constexpr u32 T = 1024;
+
+    // ---- 1. exclusive scan of the per-block root counts; next non-empty block ----
+    const u32 per = (nblocks + T - 1) / T;
+    const u32 b0 = min(tid * per, nblocks), b1 = min(b0 + per, nblocks);
+    u32 local = 0;
+    for (u32 b = b0; b < b1; ++b) local += root_count[b];
+    const u32 incl = block_scan_inclusive_1024(local, s_tmp);
+    {
+        u32 run = incl - local;
+        for (u32 b = b0; b < b1; ++b) { sc.block_off[b] = run; run += root_count[b]; }
+    }
+    if (tid == T - 1) { sc.block_off[nblocks] = incl; s_misc[0] = incl; sc.next_ne[nblocks] = nblocks; }
+    __syncthreads();
+    const u32 nroots = s_misc[0];
+    // next_ne: block_off is non-decreasing, so the next non-empty block after b is the first b' >= b with
+    // block_off[b' + 1] > block_off[b]  -> binary search
+    for (u32 b = tid; b < nblocks; b += T) {
+        const u32 base = sc.block_off[b];
+        u32 lo = b, hi = nblocks;             // find smallest lo in [b, nblocks] with block_off[lo + 1] > base
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            if (sc.block_off[mid + 1] > base) hi = mid; else lo = mid + 1;
+        }
+        sc.next_ne[b] = lo;
+    }
+    const u32 nr = static_cast<u32>((ncorr + row - 1) / row);      // A-type starts row*m < ncorr
+    const u32 ncand = nr + nroots;
+    const u32 END = ncand;
+    if (ncand + 1 > sc.cap || nr + 2 > max_positions) {
+        // too many roots for the scratch: correct-but-slow path
+        __syncthreads();
+        if (tid == 0) {
+            pick_sequential(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions, max_positions, result);
+            result->n_roots = nroots;
+        }
+        return;
+    }
+    __syncthreads();
+
+    // smallest root >= s as (dense index, position); s < ncorr guarantees one exists
+    auto first_root_dense = [&](u32 s, u32 &dense, u32 &pos) {
+        u32 b = s / dist;
+        const u32 *list = root_list + static_cast<u64>(b) * dist;
+        const u32 cnt = sc.block_off[b + 1] - sc.block_off[b];
+        u32 lo = 0, hi = cnt;
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            if (list[mid] < s) lo = mid + 1; else hi = mid;
+        }
+        if (lo < cnt) { dense = sc.block_off[b] + lo; pos = list[lo]; return; }
+        b = sc.next_ne[b + 1];
+        dense = sc.block_off[b];
+        pos = root_list[static_cast<u64>(b) * dist];
+    };
+
+    // ---- 2. the jump table J0 = F over all candidates ----
+    for (u32 c = tid; c <= ncand; c += T) {
+        u32 nxt = END, s = 0xFFFFFFFFu, peak = 0;
+        if (c < ncand) {
+            u64 s64;
+            if (c < nr) {
+                s64 = static_cast<u64>(c) * row;
+            } else {
+                // B-type: root number (c - nr) in dense order -> locate its block by binary search on block_off
+                const u32 r = c - nr;
+                u32 lo = 0, hi = nblocks;     // largest b with block_off[b] <= r  (and block non-empty)
+                while (lo + 1 < hi) {
+                    const u32 mid = (lo + hi) >> 1;
+                    if (sc.block_off[mid] <= r) lo = mid; else hi = mid;
+                }
+                // lo may point at an empty block sharing the same offset; advance to the non-empty one
+                lo = sc.next_ne[lo];
+                const u32 rp = root_list[static_cast<u64>(lo) * dist + (r - sc.block_off[lo])];
+                s64 = static_cast<u64>(rp) + dist + 1;
+            }
+            if (s64 < ncorr) {
+                s = static_cast<u32>(s64);
+                u32 dense;
+                first_root_dense(s, dense, peak);
+                const u64 sb = static_cast<u64>(peak) + dist + 1;
+                const u64 sa = static_cast<u64>(row) * (s / row + 1);
+                const u64 sn = max(sa, sb);
+                if (sn < ncorr) nxt = sb >= sa ? nr + dense : static_cast<u32>(sa / row);
+            } else {
+                s = 0xFFFFFFFFu;   // this start is never visited
+            }
+        }
+        sc.cand_s[c] = s;
+        sc.cand_peak[c] = peak;
+        sc.ja[c] = (c < ncand && s != 0xFFFFFFFFu) ? nxt : END;
+    }
+    // ---- 3. the first start, from the seed (decode.rs:208-209) ----
+    if (tid == 0) {
+        const u32 seed = result->seed_index;
+        u32 p1 = 0, start = END;
+        u64 s2 = 2ull * row;
+        if (seed != kNoSeed) {
+            u32 dense;
+            first_root_dense(seed, dense, p1);
+            const u64 sb = static_cast<u64>(p1) + dist + 1;
+            if (sb >= s2) { s2 = sb; start = nr + dense; }
+        }
+        if (s2 < ncorr) { if (start == END) start = static_cast<u32>(s2 / row); } else start = END;
+        positions[0] = p1;
+        sc.orbit[0] = start;
+        s_misc[1] = start;
+    }
+    __syncthreads();
+
+    // ---- 4. pointer doubling; orbit[n + 2^k] = J_k[orbit[n]] ----
+    u32 *jc = sc.ja, *jn = sc.jb;
+    const u32 max_events = min(nr + 1, max_positions);   // every event lands in a new row
+    for (u32 span = 1; span < max_events; span <<= 1) {
+        for (u32 n = tid; n < span && n + span < max_events; n += T) sc.orbit[n + span] = jc[sc.orbit[n]];
+        if ((span << 1) < max_events) {
+            for (u32 c0 = tid; c0 <= ncand; c0 += 8 * T) {
+                u32 a[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const u32 c = c0 + i * T; a[i] = c <= ncand ? jc[c] : END; }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = jc[a[i]];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const u32 c = c0 + i * T; if (c <= ncand) jn[c] = a[i]; }
+            }
+        }
+        __syncthreads();
+        u32 *t = jc; jc = jn; jn = t;
+    }
+
+    // ---- 5. events -> positions (decode.rs:241-253) ----
+    // END is absorbing, so the events are the prefix of orbit[] that is != END.
+    u32 my_events = 0;
+    for (u32 n = tid; n < max_events; n += T) {
+        const u32 v = sc.orbit[n];
+        if (v == END) continue;
+        ++my_events;
+        const u32 s = sc.cand_s[v];
+        const u32 target = s / row;
+        const u32 prev = n == 0 ? 1u : sc.cand_s[sc.orbit[n - 1]] / row;
+        for (u32 j = prev; j + 1 < target; ++j) positions[j] = s;      // duplicates pushed by the `while`
+        positions[target - 1] = sc.cand_peak[v];
+    }
+    const u32 events = block_scan_inclusive_1024(my_events, s_tmp);
+    if (tid == T - 1) s_misc[2] = events;
+    __syncthreads();
+    const u32 nev = s_misc[2];
+    const u32 npeaks = nev == 0 ? 1u : sc.cand_s[sc.orbit[nev - 1]] / row;
+    __syncthreads();   // positions[] complete (written by this CTA) before the row count below
+    __threadfence_block();
+
+    // ---- 6. rows that fit (decode.rs:125-127): positions are non-decreasing -> count of the passing prefix ----
+    u32 cnt = 0;
+    for (u32 i = tid; i + 1 < npeaks; i += T)
+        if (static_cast<u64>(positions[i]) + row < nwork) ++cnt;
+    const u32 total_rows = block_scan_inclusive_1024(cnt, s_tmp);
+    if (tid == T - 1) {
+        result->n_peaks = npeaks;
+        result->n_rows = total_rows;
+        result->status = npeaks < 5 ? 3u : 0u;
+        result->n_roots = nroots;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

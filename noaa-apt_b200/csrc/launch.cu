@@ -86,11 +86,42 @@ int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32
 }
 
 int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *root_list,
-                const u32 *root_count, u32 nblocks, u32 *positions, u32 max_positions, SyncResult *result) {
-    k_pick_sequential<<<1, 32, 0, c.stream>>>(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions,
-                                              max_positions, result);
+                const u32 *root_count, u32 nblocks, u32 *positions, u32 max_positions, SyncResult *result,
+                const PickScratch *scratch) {
+    if (scratch)
+        k_pick_parallel<<<1, 1024, 0, c.stream>>>(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions,
+                                                  max_positions, result, *scratch);
+    else
+        k_pick_sequential<<<1, 32, 0, c.stream>>>(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions,
+                                                  max_positions, result);
     APT_CUDA(cudaGetLastError());
     return APT_OK;
+}
+
+static size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+size_t pick_scratch_bytes(u32 max_blocks, u32 max_positions, u32 cap) {
+    return 2 * align_up((static_cast<size_t>(max_blocks) + 1) * 4) + 4 * align_up((static_cast<size_t>(cap) + 1) * 4) +
+           align_up((static_cast<size_t>(max_positions) + 1) * 4);
+}
+
+PickScratch pick_scratch_carve(void *base, u32 max_blocks, u32 max_positions, u32 cap) {
+    char *p = static_cast<char *>(base);
+    auto take = [&](size_t count) {
+        u32 *r = reinterpret_cast<u32 *>(p);
+        p += align_up(count * 4);
+        return r;
+    };
+    PickScratch s;
+    s.block_off = take(static_cast<size_t>(max_blocks) + 1);
+    s.next_ne = take(static_cast<size_t>(max_blocks) + 1);
+    s.cand_s = take(static_cast<size_t>(cap) + 1);
+    s.cand_peak = take(static_cast<size_t>(cap) + 1);
+    s.ja = take(static_cast<size_t>(cap) + 1);
+    s.jb = take(static_cast<size_t>(cap) + 1);
+    s.orbit = take(static_cast<size_t>(max_positions) + 1);
+    s.cap = cap;
+    return s;
 }
 
 int launch_gather(const LaunchCtx &c, const float *f, const u32 *positions, const SyncResult *result,

@@ -22,6 +22,17 @@ struct SyncResult {
 };
 
 
+// Global scratch of the parallel peak picker (k_pick_parallel).
+struct PickScratch {
+    u32 *block_off;    // [nblocks + 1] exclusive scan of root_count
+    u32 *next_ne;      // [nblocks + 1] smallest non-empty block >= b (nblocks if none)
+    u32 *cand_s;       // [cap + 1] start position of each candidate
+    u32 *cand_peak;    // [cap + 1] firstroot(start)
+    u32 *ja, *jb;      // [cap + 1] ping-pong jump tables
+    u32 *orbit;        // [max_positions + 1]
+    u32 cap;           // candidate capacity
+};
+
 struct LaunchCtx {
     cudaStream_t stream;
     int sm_count;
@@ -43,7 +54,11 @@ int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32
                  SyncResult *result);
 // orbit walk -> sync positions (decode.rs:241-253).
 int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *root_list,
-                const u32 *root_count, u32 nblocks, u32 *positions, u32 max_positions, SyncResult *result);
+                const u32 *root_count, u32 nblocks, u32 *positions, u32 max_positions, SyncResult *result,
+                const PickScratch *scratch /* nullptr: sequential walk */);
+// Bytes of scratch k_pick_parallel needs, and carving of one allocation into a PickScratch.
+size_t pick_scratch_bytes(u32 max_blocks, u32 max_positions, u32 cap);
+PickScratch pick_scratch_carve(void *base, u32 max_blocks, u32 max_positions, u32 cap);
 // aligned rows + final decimation (decode.rs:122-134, 158-159).  positions == nullptr: no-sync rows.
 int launch_gather(const LaunchCtx &c, const float *f, const u32 *positions, const SyncResult *result,
                   u32 fixed_rows, u32 max_rows, u32 row, u32 px, u32 dec, float *out);

@@ -278,3 +278,15 @@ def test_decode_golden_fixture():
         ref = g[f"rows_{rate}"]
         assert got.size == ref.size
         assert nerr(got, ref) <= TOL
+
+
+def test_parallel_and_sequential_picker_agree(monkeypatch):
+    # k_pick_parallel (pointer doubling) and the one-thread walk must give the same peak list
+    x = synth.apt_signal(48000, 40, seed=4)
+    _, st = oracle.decode_steps(x, 48000)
+    f = st["filtered"]
+    par = na.find_sync(na.Context(), f, 12480)
+    monkeypatch.setenv("APTB200_SEQUENTIAL_PICK", "1")
+    seq = na.find_sync(na.Context(), f, 12480)
+    assert np.array_equal(par, st["sync_pos"])
+    assert np.array_equal(seq, st["sync_pos"])
