@@ -208,6 +208,17 @@ void apt_device_free(int device, void *ptr);
 int apt_memcpy_h2d(int device, void *dst, const void *src, size_t bytes);
 int apt_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
 
+/* ----------------------------------------------------------- introspection */
+
+/* Geometry of the tiled sm_100a resampler for a ratio L/M and a tap set (DESIGN.md "Tiled polyphase
+ * kernel"); host code, no GPU.  usable == 0: the shape falls back to the generic kernel.  tile_taps
+ * (groups*usteps*8 floats, layout [group][u][r]) and group_xs (groups entries) are optional outputs. */
+typedef struct apt_tile_info {
+    uint32_t usable, groups, p_out, p_in, usteps, row_len, rows_per_tile, smem_bytes;
+} apt_tile_info;
+int apt_tile_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_tile_info *info,
+                  float *tile_taps, size_t cap_taps, uint32_t *group_xs, size_t cap_groups);
+
 /* ------------------------------------------------------------------ batch */
 
 /* Decode `count` independent recordings (all at `input_rate`, same settings), sharded

@@ -44,6 +44,11 @@ class CFilter(C.Structure):
     ]
 
 
+class CTileInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("usable", "groups", "p_out", "p_in", "usteps", "row_len", "rows_per_tile",
+                                          "smem_bytes")]
+
+
 STATUS_CB = C.CFUNCTYPE(None, C.c_float, C.c_char_p, C.c_void_p)
 
 # name -> (restype, argtypes); every symbol include/aptb200.h declares.
@@ -95,6 +100,8 @@ SIGNATURES = {
     "apt_device_free": (None, [C.c_int, C.c_void_p]),
     "apt_memcpy_h2d": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "apt_memcpy_d2h": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "apt_tile_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(CTileInfo), C.c_void_p,
+                                C.c_size_t, C.c_void_p, C.c_size_t]),
     "apt_decode_batch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, _u64p, C.c_int, C.c_uint32, C.POINTER(CSettings),
                                    C.c_int, C.POINTER(C.c_void_p), _u64p, _u64p, C.POINTER(C.c_int),
                                    C.POINTER(C.c_int), C.c_int, C.c_int]),

@@ -53,7 +53,7 @@ int free_decoder_buffers(apt_decoder *d) {
     if (d->stream) cudaStreamSynchronize(d->stream);
     for (void *p : {(void *)d->d_h, (void *)d->d_lp, (void *)d->d_one, (void *)d->d_guard, d->d_in, (void *)d->d_r,
                     (void *)d->d_e, (void *)d->d_f, (void *)d->d_corr, (void *)d->d_aligned, (void *)d->d_root_list,
-                    (void *)d->d_root_count, (void *)d->d_pos, (void *)d->d_res, (void *)d->d_out, d->d_pick})
+                    (void *)d->d_root_count, (void *)d->d_pos, (void *)d->d_res, (void *)d->d_out, d->d_pick, (void *)d->d_tile_taps, (void *)d->d_tile_xs})
         if (p) cudaFree(p);
     if (d->h_res) cudaFreeHost(d->h_res);
     for (auto e : d->ev_begin) cudaEventDestroy(e);
@@ -228,8 +228,22 @@ extern "C" int apt_resample_with_filter(const float *signal, uint64_t n, uint32_
     const LaunchCtx c{nullptr, 148};
     if (rp.polyphase) {
         const uint64_t off2 = 2 * ((static_cast<uint64_t>(rp.taps.size()) - 1) / 2);
-        APT_TRY(launch_polyphase(c, dx.p, APT_F32, n, dh.as<float>(), rp.r.l, rp.r.m, off2, rp.nout, false, 0.f, 1.f,
-                                 dy.as<float>()));
+        TilePlan tp{};
+        std::vector<float> tt;
+        std::vector<u32> xs;
+        if (!getenv("APTB200_GENERIC_RESAMPLER") && make_tile_plan(rp.r.l, rp.r.m, rp.taps, tp, tt, xs)) {
+            DevBuf dt, dg;
+            APT_TRY(dt.alloc(tt.size() * sizeof(float)));
+            APT_TRY(dg.alloc(xs.size() * sizeof(u32)));
+            APT_CUDA(cudaMemcpy(dt.p, tt.data(), tt.size() * sizeof(float), cudaMemcpyHostToDevice));
+            APT_CUDA(cudaMemcpy(dg.p, xs.data(), xs.size() * sizeof(u32), cudaMemcpyHostToDevice));
+            APT_TRY(launch_polyphase_tiled(c, dx.as<float>(), n, dh.as<float>(), dt.as<float>(), dg.as<u32>(), tp, rp.nout,
+                                           false, 0.f, 1.f, dy.as<float>()));
+            APT_CUDA(cudaDeviceSynchronize());
+        } else {
+            APT_TRY(launch_polyphase(c, dx.p, APT_F32, n, dh.as<float>(), rp.r.l, rp.r.m, off2, rp.nout, false, 0.f, 1.f,
+                                     dy.as<float>()));
+        }
     } else {
         APT_TRY(launch_fir_decimate(c, dx.p, APT_F32, dh.as<float>(), static_cast<u32>(rp.taps.size()), rp.r.m,
                                     rp.nout, dy.as<float>()));
@@ -390,6 +404,12 @@ extern "C" int apt_decoder_create(int device, uint32_t input_rate, const apt_set
     APT_CUDA(cudaMemcpy(d->d_lp, p.lp.data(), p.lp.size() * sizeof(float), cudaMemcpyHostToDevice));
     APT_CUDA(cudaMalloc(&d->d_one, sizeof(float)));
     APT_CUDA(cudaMemcpy(d->d_one, &one, sizeof(float), cudaMemcpyHostToDevice));
+    if (p.tiled) {
+        APT_CUDA(cudaMalloc(&d->d_tile_taps, p.tile_taps.size() * sizeof(float)));
+        APT_CUDA(cudaMemcpy(d->d_tile_taps, p.tile_taps.data(), p.tile_taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+        APT_CUDA(cudaMalloc(&d->d_tile_xs, p.tile_xs.size() * sizeof(u32)));
+        APT_CUDA(cudaMemcpy(d->d_tile_xs, p.tile_xs.data(), p.tile_xs.size() * sizeof(u32), cudaMemcpyHostToDevice));
+    }
     const size_t work_bytes = std::max<uint64_t>(d->max_work, 1) * sizeof(float);
     if (!p.first_polyphase) APT_CUDA(cudaMalloc(&d->d_r, work_bytes));
     APT_CUDA(cudaMalloc(&d->d_e, work_bytes));
@@ -657,6 +677,22 @@ extern "C" int apt_decode(const float *signal, uint64_t n, uint32_t input_rate, 
 extern "C" int apt_decode_pcm16(const int16_t *pcm, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
                                 float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user) {
     return decode_oneshot(pcm, APT_PCM16, n, input_rate, s, sync, out, cap, nout, cb, user);
+}
+
+// ============================================================================= introspection
+
+extern "C" int apt_tile_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_tile_info *info,
+                             float *tile_taps, size_t cap_taps, uint32_t *group_xs, size_t cap_groups) {
+    if (!taps || !info) return fail(APT_ERR_BAD_ARG, "null argument");
+    std::vector<float> h(taps, taps + ntaps), tt;
+    std::vector<u32> xs;
+    TilePlan tp{};
+    memset(info, 0, sizeof(*info));
+    if (!make_tile_plan(l, m, h, tp, tt, xs)) return APT_OK;
+    *info = apt_tile_info{1, tp.groups, tp.p_out, tp.p_in, tp.usteps, tp.row_len, tp.qt, tp.smem_bytes};
+    if (tile_taps) memcpy(tile_taps, tt.data(), std::min(cap_taps, tt.size()) * sizeof(float));
+    if (group_xs) memcpy(group_xs, xs.data(), std::min(cap_groups, xs.size()) * sizeof(u32));
+    return APT_OK;
 }
 
 // ===================================================================================== batch

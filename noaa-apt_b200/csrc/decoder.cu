@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.hpp"
@@ -51,6 +52,8 @@ int make_plan(uint32_t input_rate, const apt_settings &s, Plan &p) {
     if (st != APT_OK) return fail(st, "resampling filter cannot be designed (atten %g, delta_w %g)",
                                   (double)rf.atten, (double)rf.delta_w_pi);
     p.off2 = 2 * ((static_cast<uint64_t>(p.h.size()) - 1) / 2);
+    p.tiled = p.first_polyphase && !getenv("APTB200_GENERIC_RESAMPLER") &&
+              make_tile_plan(p.first.l, p.first.m, p.h, p.tile, p.tile_taps, p.tile_xs);
 
     // decode.rs:95-100
     const float cut = static_cast<float>(kFinalRate) / static_cast<float>(s.work_rate);
@@ -150,8 +153,12 @@ static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n,
     if (p.first_polyphase) {
         // fast_resampling + demodulate fused: r is never written (decode.rs:77,89)
         Prof pr(d, "resample_envelope");
-        APT_TRY(launch_polyphase(c, in, format, n, d->d_h, p.first.l, p.first.m, p.off2, nwork, true, p.cosphi2,
-                                 p.sinphi, d->d_e));
+        if (p.tiled && format == APT_F32 && d->d_tile_taps)
+            APT_TRY(launch_polyphase_tiled(c, static_cast<const float *>(in), n, d->d_h, d->d_tile_taps, d->d_tile_xs,
+                                           p.tile, nwork, true, p.cosphi2, p.sinphi, d->d_e));
+        else
+            APT_TRY(launch_polyphase(c, in, format, n, d->d_h, p.first.l, p.first.m, p.off2, nwork, true, p.cosphi2,
+                                     p.sinphi, d->d_e));
         if (d->cb) d->cb(0.4f, "Demodulating", d->cb_user);                 // decode.rs:87
     } else {
         {

@@ -35,6 +35,10 @@ struct Plan {
     uint32_t dec = 0;              // work_rate / 4160 when work_multiple
     Ratio last{};                  // work_rate -> 4160 for the final NoFilter resample
     std::vector<int8_t> guard;     // sync template (empty unless work_multiple)
+    bool tiled = false;            // the tiled sm_100a resampler fits this (L, M, taps)
+    TilePlan tile{};
+    std::vector<float> tile_taps;
+    std::vector<u32> tile_xs;
 };
 
 int make_plan(uint32_t input_rate, const apt_settings &s, Plan &plan);
@@ -55,6 +59,8 @@ struct apt_decoder {
     uint32_t max_blocks = 0, max_positions = 0;
 
     float *d_h = nullptr, *d_lp = nullptr, *d_one = nullptr;
+    float *d_tile_taps = nullptr;
+    aptb200::u32 *d_tile_xs = nullptr;
     int8_t *d_guard = nullptr;
     void *d_in = nullptr;          // staging for submit_host (f32 sized)
     float *d_r = nullptr;          // resampled signal, only for the L == 1 first stage

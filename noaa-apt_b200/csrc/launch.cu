@@ -5,6 +5,7 @@
 
 #include "aptb200.h"
 #include "common.hpp"
+#include "kernels_fast.cuh"
 #include "kernels_generic.cuh"
 #include "kernels_sync.cuh"
 
@@ -43,6 +44,29 @@ int launch_polyphase(const LaunchCtx &c, const void *signal, int format, u64 len
         const float *s = static_cast<const float *>(signal);
         if (envelope) k_polyphase_generic<float, true><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, nout, cosphi2, sinphi, out);
         else k_polyphase_generic<float, false><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, nout, cosphi2, sinphi, out);
+    }
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+int launch_polyphase_tiled(const LaunchCtx &c, const float *signal, u64 len, const float *raw_taps,
+                           const float *tile_taps, const u32 *group_xs, const TilePlan &tp, u64 nout, bool envelope,
+                           float cosphi2, float sinphi, float *out) {
+    if (nout == 0) return APT_OK;
+    const u64 tile_out = static_cast<u64>(tp.qt) * tp.p_out;
+    const u64 ntiles = (nout + tile_out - 1) / tile_out;
+    const unsigned grid = static_cast<unsigned>(std::min<u64>(ntiles, static_cast<u64>(c.sm_count) * 2));
+    const unsigned block = 32 * tp.groups;
+    if (envelope) {
+        auto kern = k_polyphase_tiled_f32<true>;
+        APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem_bytes)));
+        kern<<<grid, block, tp.smem_bytes, c.stream>>>(signal, len, raw_taps, tile_taps, group_xs, tp, nout, ntiles,
+                                                        cosphi2, sinphi, out);
+    } else {
+        auto kern = k_polyphase_tiled_f32<false>;
+        APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem_bytes)));
+        kern<<<grid, block, tp.smem_bytes, c.stream>>>(signal, len, raw_taps, tile_taps, group_xs, tp, nout, ntiles,
+                                                        cosphi2, sinphi, out);
     }
     APT_CUDA(cudaGetLastError());
     return APT_OK;

@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cstdint>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -31,6 +32,18 @@ struct PickScratch {
     u32 *ja, *jb;      // [cap + 1] ping-pong jump tables
     u32 *orbit;        // [max_positions + 1]
     u32 cap;           // candidate capacity
+};
+
+// Geometry of the tiled kernel for one (L, M, taps) triple; built on the host (see make_tile_plan).
+struct TilePlan {
+    u32 l, m;          // resampling ratio
+    u32 groups;        // G = L / gcd(R, L)  (= warps per CTA)
+    u32 p_out, p_in;   // outputs / inputs per super-period
+    u32 usteps;        // U: padded taps per output group (multiple of 4*KS)
+    u32 row_len;       // floats per shared-memory row: >= p_in + usteps, multiple of 4, row_len/4 odd
+    u32 qt;            // rows (super-periods) per tile
+    u32 smem_bytes;    // dynamic shared memory
+    u64 off2;          // 2*((N-1)/2), for the halo output computed from the raw taps
 };
 
 struct LaunchCtx {
@@ -62,5 +75,14 @@ PickScratch pick_scratch_carve(void *base, u32 max_blocks, u32 max_positions, u3
 // aligned rows + final decimation (decode.rs:122-134, 158-159).  positions == nullptr: no-sync rows.
 int launch_gather(const LaunchCtx &c, const float *f, const u32 *positions, const SyncResult *result,
                   u32 fixed_rows, u32 max_rows, u32 row, u32 px, u32 dec, float *out);
+
+// Builds the geometry and the zero-padded per-group tap table of the tiled polyphase kernel for
+// (l, m, taps).  Returns false when the shape does not fit the kernel (the generic kernel is used then).
+bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, std::vector<float> &tile_taps,
+                    std::vector<u32> &group_xs);
+// Tiled fast_resampling (+ envelope).  f32 samples only.
+int launch_polyphase_tiled(const LaunchCtx &c, const float *signal, u64 len, const float *raw_taps,
+                           const float *tile_taps, const u32 *group_xs, const TilePlan &tp, u64 nout, bool envelope,
+                           float cosphi2, float sinphi, float *out);
 
 }  // namespace aptb200
