@@ -211,10 +211,13 @@ int apt_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
 /* ----------------------------------------------------------- introspection */
 
 /* Geometry of the tiled sm_100a resampler for a ratio L/M and a tap set (DESIGN.md "Tiled polyphase
- * kernel"); host code, no GPU.  usable == 0: the shape falls back to the generic kernel.  tile_taps
- * (groups*usteps*8 floats, layout [group][u][r]) and group_xs (groups entries) are optional outputs. */
+ * kernel"); host code, no GPU.  usable == 0: the shape falls back to the generic kernel.  Optional
+ * outputs: tile_taps (groups*group_stride floats; per group, per loop iteration, per slice lane a record of
+ * slice_stride floats: taps of half A [4 samples][4 outputs], of half B likewise, padding) and
+ * group_xs (groups entries: first input sample of each group relative to its row). */
 typedef struct apt_tile_info {
-    uint32_t usable, groups, p_out, p_in, usteps, row_len, rows_per_tile, smem_bytes;
+    uint32_t usable, groups, p_out, p_in, usteps, row_len, rows_per_tile, smem_bytes, slices, slice_stride,
+        half_taps, shift, iters, group_stride, ctas_per_sm;
 } apt_tile_info;
 int apt_tile_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_tile_info *info,
                   float *tile_taps, size_t cap_taps, uint32_t *group_xs, size_t cap_groups);

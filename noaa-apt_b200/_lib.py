@@ -46,7 +46,8 @@ class CFilter(C.Structure):
 
 class CTileInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("usable", "groups", "p_out", "p_in", "usteps", "row_len", "rows_per_tile",
-                                          "smem_bytes")]
+                                          "smem_bytes", "slices", "slice_stride", "half_taps", "shift", "iters",
+                                          "group_stride", "ctas_per_sm")]
 
 
 STATUS_CB = C.CFUNCTYPE(None, C.c_float, C.c_char_p, C.c_void_p)

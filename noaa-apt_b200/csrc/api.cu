@@ -68,7 +68,7 @@ int alloc_sync_buffers(apt_decoder *d) {
     if (!p.work_multiple || d->max_work <= p.guard.size()) return APT_OK;
     d->max_corr = d->max_work - p.guard.size();
     d->max_blocks = static_cast<uint32_t>((d->max_corr + p.dist - 1) / p.dist);
-    d->max_positions = static_cast<uint32_t>(d->max_work / p.row + 2);
+    d->max_positions = static_cast<uint32_t>(d->max_work / p.row + 4);
     APT_CUDA(cudaMalloc(&d->d_guard, p.guard.size()));
     APT_CUDA(cudaMemcpy(d->d_guard, p.guard.data(), p.guard.size(), cudaMemcpyHostToDevice));
     APT_CUDA(cudaMalloc(&d->d_corr, d->max_corr * sizeof(float)));
@@ -80,6 +80,7 @@ int alloc_sync_buffers(apt_decoder *d) {
     const u32 cap = static_cast<u32>(std::min<uint64_t>(static_cast<uint64_t>(d->max_positions) * 17 + 65536, 1u << 28));
     APT_CUDA(cudaMalloc(&d->d_pick, pick_scratch_bytes(d->max_blocks, d->max_positions, cap)));
     d->pick = pick_scratch_carve(d->d_pick, d->max_blocks, d->max_positions, cap);
+    APT_CUDA(cudaMemset(d->pick.ticket, 0, 8));
     if (getenv("APTB200_SEQUENTIAL_PICK")) d->use_parallel_pick = false;
     return APT_OK;
 }
@@ -689,7 +690,8 @@ extern "C" int apt_tile_plan(uint32_t l, uint32_t m, const float *taps, size_t n
     TilePlan tp{};
     memset(info, 0, sizeof(*info));
     if (!make_tile_plan(l, m, h, tp, tt, xs)) return APT_OK;
-    *info = apt_tile_info{1, tp.groups, tp.p_out, tp.p_in, tp.usteps, tp.row_len, tp.qt, tp.smem_bytes};
+    *info = apt_tile_info{1, tp.groups, tp.p_out, tp.p_in, tp.usteps, tp.row_len, tp.qt, tp.smem_bytes, 4,
+                          tp.slice_stride, tp.half_taps, tp.shift, tp.iters, tp.group_stride, tp.ctas_per_sm};
     if (tile_taps) memcpy(tile_taps, tt.data(), std::min(cap_taps, tt.size()) * sizeof(float));
     if (group_xs) memcpy(group_xs, xs.data(), std::min(cap_groups, xs.size()) * sizeof(u32));
     return APT_OK;

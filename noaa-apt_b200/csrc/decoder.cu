@@ -132,7 +132,8 @@ int run_find_sync(apt_decoder *d, uint64_t nwork) {
     }
     {
         Prof pr(d, "sync_roots");
-        APT_TRY(launch_roots(c, d->d_corr, ncorr, p.dist, d->d_root_list, d->d_root_count, d->d_res));
+        APT_TRY(launch_roots(c, d->d_corr, ncorr, p.dist, d->d_root_list, d->d_root_count, d->d_res,
+                             d->use_parallel_pick && d->d_pick ? &d->pick : nullptr));
     }
     {
         Prof pr(d, "sync_pick");

@@ -1,24 +1,25 @@
 // Tiled polyphase resampler fused with the envelope demodulator -- the hot kernel of the path
 // (fast_resampling dsp.rs:186-289 + demodulate dsp.rs:350-383), written for sm_100a.
 //
-// Formulation.  y[k] = sum_x h[x*L - k*M] * X[x].  Outputs k and k + P_out (P_out = lcm(R, L)) use the
-// same taps on inputs shifted by P_in = P_out*M/L, so the work is a small dense product per "group"
-//     acc[r][q] += T_g[u][r] * X[tile_x0 + q*P_in + xs_g + u]        r < R, q < QT, u < U
-// where group g covers the R consecutive outputs R*g .. R*g+R-1 of a super-period, xs_g is the first
-// input sample any of them touches (rounded down to a multiple of 4 for 16-byte loads) and T_g is the
-// zero-padded slice of h those outputs see.  G = L/gcd(R, L) groups cover every phase.
+// Formulation.  y[k] = sum_x h[x*L - k*M] * X[x].  Outputs k and k + P_out (P_out = lcm(8, L)) use the
+// same taps on inputs shifted by P_in = P_out*M/L, so per "group" g (outputs 8g..8g+7 of a super-period)
+//     acc[r][q] += T_g[u][r] * X[tile_x0 + q*P_in + w0_g + u]        r < 8, q < QT
+// with w0_g the first input sample the group touches (rounded down to a multiple of 4 for 16-byte loads)
+// and T_g the zero-padded slice of h its outputs see.  The group's two halves (outputs 0..3 / 4..7) have
+// windows offset by `shift` samples, so the first shift/16 loop iterations skip half B and the last skip A.
 //
-// Mapping.  One persistent CTA per SM slot (2 per SM), one warp per group.  A warp's 32 lanes are
-// KS=4 slices of the u range x 8 row lanes; each thread owns R=8 outputs x Q=4 rows (32 accumulators):
-//   - samples: rows of the input tile in shared memory, one 16-byte LDS.128 per row per 4 taps; the
-//     8 row lanes of a quarter-warp hit 8 distinct 16-byte bank groups because the row pitch/4 is odd;
-//   - taps: 8 per u step by two warp-broadcast LDS.128 (4 distinct addresses per warp);
-//   - 32 FFMA per u step per thread; fp32 accumulation in ascending u inside a slice, the 4 slices are
-//     then combined by a shuffle reduce-scatter (24 SHFL per thread per tile).
-// Input rows and the tap table are staged by 1-D TMA bulk copies (cp.async.bulk, one row per lane,
-// completion on an mbarrier); the CTA's other resident CTA on the SM computes meanwhile.
-// Epilogue: the tile of resampled values is parked in the (now free) row buffer, then every thread
-// turns (r[k-1], r[k]) into the envelope and stores it coalesced -- r itself never reaches HBM.
+// Mapping.  Persistent CTAs (2 per SM when shared memory allows), one warp per group.  A warp's 32 lanes
+// are KS=4 interleaved slices of the sample axis x 8 row lanes; a thread owns 8 outputs x 4 rows
+// (32 accumulators) and, per loop iteration, one 16-byte chunk of each of its rows:
+//   - samples: LDS.128 from the row tile; the 8 row lanes of a quarter-warp hit 8 distinct 16-byte bank
+//     groups because the row pitch/4 is odd;
+//   - taps: 8 LDS.128 per iteration, warp-broadcast with 4 distinct addresses skewed across bank groups;
+//   - 128 FFMA per iteration; fp32, ascending sample order within a slice.
+// Input rows and the tap table arrive by 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) completing on an
+// mbarrier; the next tile's rows are prefetched into L2 meanwhile.  The four slices' partial sums meet in
+// shared memory (the row buffer is free by then), and the epilogue turns (r[k-1], r[k]) into the envelope
+// and stores float4 -- the resampled signal itself never reaches HBM.  r[K0-1] comes from one extra
+// "virtual" row holding the window of the last group of the previous super-period.
 #pragma once
 
 #include <cstdint>
@@ -59,31 +60,53 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, u32 byt
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// warm L2 with a span of global memory (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2(const void *src, u32 bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 
-constexpr int kTileR = 8, kTileQ = 4, kTileKS = 4;
+constexpr int kTileR = 8, kTileH = 4, kTileQ = 4, kTileKS = 4;
 constexpr int kTileRowLanes = 32 / kTileKS;           // 8
 constexpr int kTileQT = kTileRowLanes * kTileQ;       // 32 rows per tile
 
-// group_xs[g] = xs'_g, the (4-aligned) first input sample of group g relative to its row.
-// f32 instantiation of the tile kernel.  (PCM16 input goes through the generic kernel for now.)
+// one half (4 outputs) x 4 rows x 4 consecutive samples
+__device__ __forceinline__ void half_fma(float (&acc)[kTileH][kTileQ], const float4 *__restrict__ t,
+                                         const float4 (&s)[kTileQ]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float4 tp = t[u];                      // taps of outputs r = 0..3 for sample u of the chunk
+#pragma unroll
+        for (int j = 0; j < kTileQ; ++j) {
+            const float sv = u == 0 ? s[j].x : u == 1 ? s[j].y : u == 2 ? s[j].z : s[j].w;
+            acc[0][j] = fmaf(tp.x, sv, acc[0][j]);
+            acc[1][j] = fmaf(tp.y, sv, acc[1][j]);
+            acc[2][j] = fmaf(tp.z, sv, acc[2][j]);
+            acc[3][j] = fmaf(tp.w, sv, acc[3][j]);
+        }
+    }
+}
+
+// group_xs[g] = w0_g, the (4-aligned) first input sample of group g relative to its row.
 template <bool ENVELOPE>
 __global__ void __launch_bounds__(32 * 13, 2)
-k_polyphase_tiled_f32(const float *__restrict__ signal, u64 len, const float *__restrict__ raw_taps,
-                      const float *__restrict__ tile_taps, const u32 *__restrict__ group_xs, TilePlan tp, u64 nout,
-                      u64 ntiles, float cosphi2, float sinphi, float *__restrict__ out) {
-    constexpr int R = kTileR, Q = kTileQ, KS = kTileKS, QT = kTileQT;
+k_polyphase_tiled_f32(const float *__restrict__ signal, u64 len, const float *__restrict__ tile_taps,
+                      const u32 *__restrict__ group_xs, TilePlan tp, u64 nout, u64 ntiles, float cosphi2,
+                      float sinphi, float *__restrict__ out) {
+    constexpr int H = kTileH, Q = kTileQ, KS = kTileKS, QT = kTileQT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [mbarrier 16 B][taps G*U*R][rows QT*row_len]
+    // layout: [mbarrier 16 B][taps G*group_stride][rows / partial-sum planes][virtual halo row]
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem_raw);
     float *s_taps = reinterpret_cast<float *>(smem_raw + 16);
-    const u32 taps_floats = tp.groups * tp.usteps * R;
+    const u32 taps_floats = tp.groups * tp.group_stride;
     float *s_rows = s_taps + taps_floats;
+    float *s_vrow = s_rows + tp.rows_floats;
     __shared__ float s_halo;                      // r[K0 - 1]
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 ks = lane >> 3, ql = lane & 7;
     const u32 nthreads = blockDim.x;
     const u32 tile_out = QT * tp.p_out;
+    const float inv_sinphi = 1.f / sinphi;
 
     u32 phase = 0;
     if (tid == 0) {
@@ -91,141 +114,167 @@ k_polyphase_tiled_f32(const float *__restrict__ signal, u64 len, const float *__
         fence_mbar_init();
     }
     __syncthreads();
-    // tap table: one bulk copy for the whole CTA lifetime
+    // tap table: bulk copies once per CTA lifetime
     if (tid == 0) {
         fence_proxy_async();
-        mbar_expect_tx(bar, taps_floats * 4);
-        // bulk copies are limited in size only by the tx-count field (2^20-1 bytes); split to be safe
-        u32 done = 0;
         const u32 total = taps_floats * 4;
-        while (done < total) {
-            const u32 chunk = min(total - done, 32768u);
+        mbar_expect_tx(bar, total);
+        for (u32 done = 0; done < total; done += 32768u)
             tma_bulk_g2s(reinterpret_cast<unsigned char *>(s_taps) + done,
-                         reinterpret_cast<const unsigned char *>(tile_taps) + done, chunk, bar);
-            done += chunk;
-        }
+                         reinterpret_cast<const unsigned char *>(tile_taps) + done, min(total - done, 32768u), bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
 
-    const u32 xs_g = warp < tp.groups ? group_xs[warp] : 0;
-    const u32 ul = tp.usteps / KS;                // u steps per slice (multiple of 4)
-    const bool aligned16 = (reinterpret_cast<uintptr_t>(signal) & 15) == 0 && (tp.p_in & 3) == 0;
+    const u32 w0 = group_xs[warp];
+    const u32 w0_last = group_xs[tp.groups - 1];
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(signal) & 15) == 0;
+    const u32 it_a_end = tp.half_taps / 16;       // half A is active for iterations [0, it_a_end)
+    const u32 it_b_begin = tp.shift / 16;         // half B for [it_b_begin, iters)
 
     for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const u64 k_base = tile * tile_out;                       // first output of the tile
         const u64 x_base = tile * static_cast<u64>(QT) * tp.p_in; // first input sample of row 0
-        // ---- stage the input rows ----
-        const u64 x_last = x_base + static_cast<u64>(QT - 1) * tp.p_in + tp.row_len;   // one past the last sample needed
-        const bool interior = aligned16 && x_last <= len;
-        if (interior) {
-            if (warp == 0) {
-                fence_proxy_async();              // rows were last touched through the generic proxy
-                if (lane == 0) mbar_expect_tx(bar, QT * tp.row_len * 4);
-                __syncwarp();
-                tma_bulk_g2s(s_rows + lane * tp.row_len, signal + x_base + static_cast<u64>(lane) * tp.p_in,
-                             tp.row_len * 4, bar);
+        // ---- stage the input rows (+ the virtual halo row) ----
+        const u64 x_end = x_base + static_cast<u64>(QT - 1) * tp.p_in + tp.row_len;   // one past the last sample
+        const bool interior = aligned16 && x_end <= len;
+        const bool want_halo = ENVELOPE && k_base > 0;
+        const u64 x_halo = x_base - tp.p_in + w0_last;            // only meaningful when k_base > 0
+        if (tp.debug == 2) {
+            __syncthreads();
+        } else if (interior) {
+            if (tid == 0) {
+                fence_proxy_async();              // the buffer was last touched through the generic proxy
+                mbar_expect_tx(bar, (QT * tp.row_len + (want_halo ? tp.usteps : 0)) * 4);
             }
+            if (lane == 0) {
+                fence_proxy_async();
+                for (u32 q = warp; q < QT; q += tp.groups) {
+                    tma_bulk_g2s(s_rows + q * tp.row_len, signal + x_base + static_cast<u64>(q) * tp.p_in,
+                                 tp.row_len * 4, bar);
+                    // pull the same row of this CTA's next tile into L2 while this one is being computed
+                    const u64 nx = x_base + (static_cast<u64>(gridDim.x) * QT + q) * tp.p_in;
+                    if (tile + gridDim.x < ntiles && nx + tp.p_in <= len) tma_prefetch_l2(signal + nx, tp.p_in * 4);
+                }
+                if (want_halo && warp == tp.groups - 1) tma_bulk_g2s(s_vrow, signal + x_halo, tp.usteps * 4, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
         } else {
             for (u32 i = tid; i < QT * tp.row_len; i += nthreads) {
                 const u32 q = i / tp.row_len, c = i - q * tp.row_len;
                 const u64 x = x_base + static_cast<u64>(q) * tp.p_in + c;
                 s_rows[i] = x < len ? __ldg(signal + x) : 0.f;    // past the end: signal.get(x) == None
             }
+            if (want_halo)
+                for (u32 i = tid; i < tp.usteps; i += nthreads) s_vrow[i] = x_halo + i < len ? __ldg(signal + x_halo + i) : 0.f;
+            __syncthreads();
         }
-        // ---- r[K0 - 1] for the envelope of the tile's first output (raw taps, straight from global) ----
-        if (ENVELOPE && warp == tp.groups - 1) {
+
+        // ---- r[K0 - 1]: output 7 of the last group of the previous super-period, from the virtual row ----
+        if (ENVELOPE && warp == 0) {
             float part = 0.f;
-            if (k_base > 0) {
-                const u64 k = k_base - 1;
-                const u64 t0 = k * tp.m;
-                u64 x = (t0 + tp.l - 1) / tp.l;
-                u64 xe = (t0 + tp.off2) / tp.l;
-                if (xe >= len) xe = len - 1;
-                for (u64 xi = x + lane; xi <= xe; xi += 32)
-                    part = fmaf(__ldg(raw_taps + (xi * tp.l - t0)), __ldg(signal + xi), part);
+            if (want_halo) {
+                const float *tg = s_taps + static_cast<size_t>(tp.groups - 1) * tp.group_stride;
+                for (u32 u = tp.shift + lane; u < tp.usteps; u += 32) {
+                    const u32 chunk = u >> 2, uu = u & 3;            // chunk = it*KS + ks
+                    part = fmaf(tg[chunk * tp.slice_stride + 16 + uu * H + 3], s_vrow[u], part);
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
             if (lane == 0) s_halo = part;
         }
-        if (interior) {
-            mbar_wait(bar, phase);
-            phase ^= 1;
-        } else {
-            __syncthreads();
-        }
 
-        // ---- the product: R x Q accumulators per thread over this lane's slice of u ----
-        float acc[R][Q];
+        // ---- the product: 8 x 4 accumulators per thread over this lane's chunks ----
+        float acc_a[H][Q], acc_b[H][Q];
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int r = 0; r < H; ++r)
 #pragma unroll
-            for (int j = 0; j < Q; ++j) acc[r][j] = 0.f;
-        if (warp < tp.groups) {
-            const u32 u0 = ks * ul;
-            const float4 *tap4 = reinterpret_cast<const float4 *>(s_taps + (static_cast<size_t>(warp) * tp.usteps + u0) * R);
-            const float *row0 = s_rows + xs_g + u0;
+            for (int j = 0; j < Q; ++j) acc_a[r][j] = acc_b[r][j] = 0.f;
+        if (tp.debug != 1) {
+            const float4 *tap4 = reinterpret_cast<const float4 *>(s_taps + static_cast<size_t>(warp) * tp.group_stride +
+                                                                  ks * tp.slice_stride);
+            const u32 tap_it = KS * tp.slice_stride / 4;           // float4 per iteration
             const float4 *rp[Q];
 #pragma unroll
-            for (int j = 0; j < Q; ++j) rp[j] = reinterpret_cast<const float4 *>(row0 + (ql + 8 * j) * tp.row_len);
-            for (u32 c = 0; c < ul / 4; ++c) {
+            for (int j = 0; j < Q; ++j)
+                rp[j] = reinterpret_cast<const float4 *>(s_rows + (ql + 8 * j) * tp.row_len + w0) + ks;
+            u32 it = 0;
+            for (; it < it_b_begin; ++it) {                        // half A only
                 float4 s[Q];
 #pragma unroll
-                for (int j = 0; j < Q; ++j) s[j] = rp[j][c];
+                for (int j = 0; j < Q; ++j) s[j] = rp[j][it * KS];
+                half_fma(acc_a, tap4 + it * tap_it, s);
+            }
+            for (; it < it_a_end; ++it) {                          // both halves
+                float4 s[Q];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 ta = tap4[(c * 4 + i) * 2], tb = tap4[(c * 4 + i) * 2 + 1];
-                    const float t[R] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+                for (int j = 0; j < Q; ++j) s[j] = rp[j][it * KS];
+                half_fma(acc_a, tap4 + it * tap_it, s);
+                half_fma(acc_b, tap4 + it * tap_it + 4, s);
+            }
+            for (; it < tp.iters; ++it) {                          // half B only
+                float4 s[Q];
 #pragma unroll
-                    for (int j = 0; j < Q; ++j) {
-                        const float sv = i == 0 ? s[j].x : i == 1 ? s[j].y : i == 2 ? s[j].z : s[j].w;
-#pragma unroll
-                        for (int r = 0; r < R; ++r) acc[r][j] = fmaf(t[r], sv, acc[r][j]);
-                    }
-                }
+                for (int j = 0; j < Q; ++j) s[j] = rp[j][it * KS];
+                half_fma(acc_b, tap4 + it * tap_it + 4, s);
             }
         }
-        // ---- combine the KS slices: reduce-scatter over lanes ks (xor 16, xor 8) ----
-        // flat index i = r*Q + j; after both rounds lane ks owns flat indices [ks*8, ks*8+8)
-        float h1[16];
+        __syncthreads();   // every warp is done reading the rows: the buffer now takes the partial sums
+
+        // ---- partial sums of the 4 slices -> planes [ks][row][plane_pitch] ----
+        float *s_plane = s_rows;
+        const u32 plane_floats = QT * tp.plane_pitch;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float lo = acc[i / Q][i % Q], hi = acc[(i + 16) / Q][(i + 16) % Q];
-            const float send = (ks & 2) ? lo : hi;
-            const float keep = (ks & 2) ? hi : lo;
-            h1[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        for (int j = 0; j < Q; ++j) {
+            float *dst = s_plane + ks * plane_floats + (ql + 8 * j) * tp.plane_pitch + warp * kTileR;
+            *reinterpret_cast<float4 *>(dst) = make_float4(acc_a[0][j], acc_a[1][j], acc_a[2][j], acc_a[3][j]);
+            *reinterpret_cast<float4 *>(dst + 4) = make_float4(acc_b[0][j], acc_b[1][j], acc_b[2][j], acc_b[3][j]);
         }
-        float h2[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float send = (ks & 1) ? h1[i] : h1[i + 8];
-            const float keep = (ks & 1) ? h1[i + 8] : h1[i];
-            h2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-        __syncthreads();   // every warp is done reading the rows: park the resampled tile there
-        float *s_r = s_rows;                       // s_r[1 + k_local], s_r[0] = halo
-        if (warp < tp.groups) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const u32 flat = ks * 8 + i;       // = r*Q + j
-                const u32 r = flat / Q, j = flat % Q;
-                const u32 q = ql + 8 * j;
-                s_r[1 + q * tp.p_out + warp * R + r] = h2[i];
-            }
-        }
-        if (tid == 0) s_r[0] = ENVELOPE ? s_halo : 0.f;
         __syncthreads();
-        // ---- epilogue: envelope (dsp.rs:373) and coalesced store ----
-        for (u32 kl = tid; kl < tile_out; kl += nthreads) {
-            const u64 k = k_base + kl;
-            if (k >= nout) break;
-            float v;
-            if (ENVELOPE) v = k == 0 ? 0.f : envelope2(s_r[kl], s_r[kl + 1], cosphi2, sinphi);
-            else v = s_r[kl + 1];
-            out[k] = v;
+        // ---- reduce the planes into plane 0 (4 outputs per thread-iteration) ----
+        const u32 vec_per_row = tp.p_out / 4;
+        const u32 nvec = QT * vec_per_row;
+        for (u32 v = tid; v < nvec; v += nthreads) {
+            const u32 q = v / vec_per_row, c4 = v - q * vec_per_row;
+            float4 *p0 = reinterpret_cast<float4 *>(s_plane + q * tp.plane_pitch) + c4;
+            const float4 a = *p0;
+            const float4 b = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p0) + plane_floats);
+            const float4 c = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p0) + 2 * plane_floats);
+            const float4 d = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p0) + 3 * plane_floats);
+            *p0 = make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z),
+                              (a.w + b.w) + (c.w + d.w));
         }
-        __syncthreads();   // rows buffer is free for the next tile's bulk copies
+        __syncthreads();
+        // ---- epilogue: envelope (dsp.rs:373) and 16-byte stores ----
+        for (u32 v = tid; v < nvec; v += nthreads) {
+            const u32 q = v / vec_per_row, c4 = v - q * vec_per_row;
+            const u64 k = k_base + static_cast<u64>(q) * tp.p_out + 4 * c4;
+            if (k >= nout) continue;
+            const float *row = s_plane + q * tp.plane_pitch;
+            const float4 cur = *reinterpret_cast<const float4 *>(row + 4 * c4);
+            float4 res = cur;
+            if (ENVELOPE) {
+                float prev;
+                if (c4 > 0) prev = row[4 * c4 - 1];
+                else if (q > 0) prev = row[-static_cast<int>(tp.plane_pitch) + static_cast<int>(tp.p_out) - 1];
+                else prev = s_halo;
+                res.x = k == 0 ? 0.f : envelope2_fast(prev, cur.x, cosphi2, inv_sinphi);
+                res.y = envelope2_fast(cur.x, cur.y, cosphi2, inv_sinphi);
+                res.z = envelope2_fast(cur.y, cur.z, cosphi2, inv_sinphi);
+                res.w = envelope2_fast(cur.z, cur.w, cosphi2, inv_sinphi);
+            }
+            if (k + 4 <= nout && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+                *reinterpret_cast<float4 *>(out + k) = res;
+            } else {
+                out[k] = res.x;
+                if (k + 1 < nout) out[k + 1] = res.y;
+                if (k + 2 < nout) out[k + 2] = res.z;
+                if (k + 3 < nout) out[k + 3] = res.w;
+            }
+        }
+        __syncthreads();   // the buffer is free for the next tile's bulk copies
     }
 }
 

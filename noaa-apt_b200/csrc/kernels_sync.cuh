@@ -24,6 +24,9 @@ namespace aptb200 {
 
 constexpr u32 kNoSeed = 0xFFFFFFFFu;
 
+__device__ __forceinline__ bool last_cta_arrives(u32 *ticket);
+__device__ void scan_root_counts(const u32 *root_count, u32 nblocks, u32 *block_off);
+
 // ---------------------------------------------------------------------------------------------
 // k_roots: block b owns positions [b*D, (b+1)*D).  For p in the block the window (p, p+D] splits
 // into the rest of the block (suffix maximum) and a prefix of the next block (prefix maximum).
@@ -33,7 +36,8 @@ constexpr u32 kNoSeed = 0xFFFFFFFFu;
 template <int THREADS, int CHUNK>
 __global__ void __launch_bounds__(THREADS)
 k_roots(const float *__restrict__ corr, u64 ncorr, u32 dist, u32 *__restrict__ root_list,
-        u32 *__restrict__ root_count, SyncResult *__restrict__ result) {
+        u32 *__restrict__ root_count, SyncResult *__restrict__ result, u32 *__restrict__ block_off,
+        u32 *__restrict__ ticket) {
     extern __shared__ float sm[];
     float *a = sm;             // a[0..D): this block, a[D..2D): next block (later: its prefix maxima)
     __shared__ float s_suffix[THREADS];   // max of chunks strictly to the right, within this block
@@ -125,6 +129,8 @@ k_roots(const float *__restrict__ corr, u64 ncorr, u32 dist, u32 *__restrict__ r
         if (flags & (1u << c)) list[w++] = static_cast<u32>(base + lo + c);
     if (tid == THREADS - 1) root_count[blockIdx.x] = s_count[THREADS - 1];
     if (blockIdx.x == 0 && tid == 0) result->seed_index = s_seed;
+    // the last CTA to finish numbers the roots densely (exclusive scan of the per-block counts)
+    if (ticket != nullptr && last_cta_arrives(ticket)) scan_root_counts(root_count, gridDim.x, block_off);
 }
 
 // Smallest root >= s.  Binary search in the block of s, then the first root of the following
@@ -189,15 +195,16 @@ __global__ void k_pick_sequential(u64 ncorr, u64 nwork, u32 row, u32 dist, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_pick_parallel: the orbit of F by pointer doubling, one CTA of 1024 threads.
+// Parallel picker: the orbit of F by pointer doubling.
 //
-// Candidate starts: A_m = row*m (m < NR) and B_r = root_r + D + 1 (one per root) -- F maps every
-// start onto one of these, so F is a table J0 over NR + nroots nodes (+ END).  Level k holds
-// J_k = F^(2^k); the orbit is grown by  orbit[n + 2^k] = J_k[orbit[n]]  for n < 2^k, so only the
-// current level is needed.  All tables live in global scratch (L2-resident, a few hundred KB).
-// Falls back to the sequential walk when the candidate count exceeds the scratch capacity.
+// Candidate starts: A_m = row*m (m < NR) and B_r = root_r + D + 1 (one per root, r in dense order) --
+// F maps every start onto one of these, so F is a table J0 over NR + nroots nodes (+ END).
+//   k_roots' last CTA     : exclusive scan of the per-block root counts -> dense root numbering
+//   k_pick_links (grid)   : J0[c] = F(c), start position and peak of every candidate, one thread each
+//   k_pick_links' last CTA: J_{k+1} = J_k o J_k in shared memory (global if it does not fit) while the
+//                           orbit grows by orbit[n + 2^k] = J_k[orbit[n]]; then events -> positions.
+// Falls back to the one-thread walk when the candidates exceed the scratch capacity.
 // ---------------------------------------------------------------------------------------------
-
 __device__ __forceinline__ u32 block_scan_inclusive_1024(u32 v, u32 *s_tmp) {
     // inclusive scan of one value per thread over a 1024-thread CTA
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -223,125 +230,136 @@ __device__ __forceinline__ u32 block_scan_inclusive_1024(u32 v, u32 *s_tmp) {
     return v;
 }
 
+// True in exactly one CTA of the grid: the last one to arrive.  Resets the ticket for the next launch.
+__device__ __forceinline__ bool last_cta_arrives(u32 *ticket) {
+    __shared__ u32 s_is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const u32 t = atomicAdd(ticket, 1u);
+        s_is_last = t == gridDim.x - 1;
+        if (s_is_last) *ticket = 0;
+    }
+    __syncthreads();
+    if (s_is_last) __threadfence();
+    return s_is_last != 0;
+}
+
+// Exclusive scan of root_count[0..nblocks) into block_off[0..nblocks]; 1024 threads.
+__device__ void scan_root_counts(const u32 *root_count, u32 nblocks, u32 *block_off) {
+    __shared__ u32 s_tmp[32];
+    constexpr u32 T = 1024;
+    const u32 tid = threadIdx.x;
+    const u32 per = (nblocks + T - 1) / T;
+    const u32 b0 = min(tid * per, nblocks), b1 = min(b0 + per, nblocks);
+    u32 local = 0;
+    for (u32 b = b0; b < b1; ++b) local += __ldcg(root_count + b);
+    const u32 incl = block_scan_inclusive_1024(local, s_tmp);
+    u32 run = incl - local;
+    for (u32 b = b0; b < b1; ++b) { block_off[b] = run; run += __ldcg(root_count + b); }
+    if (tid == T - 1) block_off[nblocks] = incl;
+}
+
+// smallest root >= s as (dense index, position); s < ncorr guarantees one exists
+__device__ __forceinline__ void first_root_dense(u32 s, u32 dist, u32 nblocks, const u32 *__restrict__ root_list,
+                                                 const u32 *__restrict__ block_off, u32 &dense, u32 &pos) {
+    u32 b = s / dist;
+    const u32 *list = root_list + static_cast<u64>(b) * dist;
+    u32 base = block_off[b];
+    const u32 cnt = block_off[b + 1] - base;
+    u32 lo = 0, hi = cnt;
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (list[mid] < s) lo = mid + 1; else hi = mid;
+    }
+    if (lo < cnt) { dense = base + lo; pos = list[lo]; return; }
+    // first root of the next non-empty block
+    const u32 want = block_off[b + 1];
+    ++b;
+    while (b < nblocks && block_off[b + 1] == want) ++b;
+    dense = want;
+    pos = b < nblocks ? root_list[static_cast<u64>(b) * dist] : 0xFFFFFFFFu;
+}
+
 __global__ void __launch_bounds__(1024)
-k_pick_parallel(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ root_list,
-                const u32 *__restrict__ root_count, u32 nblocks, u32 *__restrict__ positions, u32 max_positions,
-                SyncResult *__restrict__ result, PickScratch sc) {
+k_pick_links(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ root_list,
+             const u32 *__restrict__ root_count, u32 nblocks, u32 *__restrict__ positions, u32 max_positions,
+             SyncResult *__restrict__ result, PickScratch sc, u32 smem_words) {
+    extern __shared__ u32 s_tab[];
     __shared__ u32 s_tmp[32];
     __shared__ u32 s_misc[4];
     const u32 tid = threadIdx.x;
     constexpr u32 T = 1024;
-
-    // ---- 1. exclusive scan of the per-block root counts; next non-empty block ----
-    const u32 per = (nblocks + T - 1) / T;
-    const u32 b0 = min(tid * per, nblocks), b1 = min(b0 + per, nblocks);
-    u32 local = 0;
-    for (u32 b = b0; b < b1; ++b) local += root_count[b];
-    const u32 incl = block_scan_inclusive_1024(local, s_tmp);
-    {
-        u32 run = incl - local;
-        for (u32 b = b0; b < b1; ++b) { sc.block_off[b] = run; run += root_count[b]; }
-    }
-    if (tid == T - 1) { sc.block_off[nblocks] = incl; s_misc[0] = incl; sc.next_ne[nblocks] = nblocks; }
-    __syncthreads();
-    const u32 nroots = s_misc[0];
-    // next_ne: block_off is non-decreasing, so the next non-empty block after b is the first b' >= b with
-    // block_off[b' + 1] > block_off[b]  -> binary search
-    for (u32 b = tid; b < nblocks; b += T) {
-        const u32 base = sc.block_off[b];
-        u32 lo = b, hi = nblocks;             // find smallest lo in [b, nblocks] with block_off[lo + 1] > base
-        while (lo < hi) {
-            const u32 mid = (lo + hi) >> 1;
-            if (sc.block_off[mid + 1] > base) hi = mid; else lo = mid + 1;
-        }
-        sc.next_ne[b] = lo;
-    }
+    const u32 nroots = sc.block_off[nblocks];
     const u32 nr = static_cast<u32>((ncorr + row - 1) / row);      // A-type starts row*m < ncorr
     const u32 ncand = nr + nroots;
     const u32 END = ncand;
-    if (ncand + 1 > sc.cap || nr + 2 > max_positions) {
-        // too many roots for the scratch: correct-but-slow path
-        __syncthreads();
-        if (tid == 0) {
+    if (ncand + 1 > sc.cap || nr + 1 > max_positions) {
+        // too many roots for the scratch (e.g. silence: every index is a root): correct-but-slow path
+        if (blockIdx.x == 0 && tid == 0) {
             pick_sequential(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions, max_positions, result);
             result->n_roots = nroots;
         }
         return;
     }
-    __syncthreads();
 
-    // smallest root >= s as (dense index, position); s < ncorr guarantees one exists
-    auto first_root_dense = [&](u32 s, u32 &dense, u32 &pos) {
-        u32 b = s / dist;
-        const u32 *list = root_list + static_cast<u64>(b) * dist;
-        const u32 cnt = sc.block_off[b + 1] - sc.block_off[b];
-        u32 lo = 0, hi = cnt;
-        while (lo < hi) {
-            const u32 mid = (lo + hi) >> 1;
-            if (list[mid] < s) lo = mid + 1; else hi = mid;
-        }
-        if (lo < cnt) { dense = sc.block_off[b] + lo; pos = list[lo]; return; }
-        b = sc.next_ne[b + 1];
-        dense = sc.block_off[b];
-        pos = root_list[static_cast<u64>(b) * dist];
-    };
-
-    // ---- 2. the jump table J0 = F over all candidates ----
-    for (u32 c = tid; c <= ncand; c += T) {
+    // ---- J0 = F for this thread's candidate ----
+    const u32 c = blockIdx.x * T + tid;
+    if (c <= ncand) {
         u32 nxt = END, s = 0xFFFFFFFFu, peak = 0;
         if (c < ncand) {
             u64 s64;
             if (c < nr) {
                 s64 = static_cast<u64>(c) * row;
             } else {
-                // B-type: root number (c - nr) in dense order -> locate its block by binary search on block_off
-                const u32 r = c - nr;
-                u32 lo = 0, hi = nblocks;     // largest b with block_off[b] <= r  (and block non-empty)
+                const u32 r = c - nr;                      // dense root number -> its block
+                u32 lo = 0, hi = nblocks;                  // largest b with block_off[b] <= r
                 while (lo + 1 < hi) {
                     const u32 mid = (lo + hi) >> 1;
                     if (sc.block_off[mid] <= r) lo = mid; else hi = mid;
                 }
-                // lo may point at an empty block sharing the same offset; advance to the non-empty one
-                lo = sc.next_ne[lo];
                 const u32 rp = root_list[static_cast<u64>(lo) * dist + (r - sc.block_off[lo])];
                 s64 = static_cast<u64>(rp) + dist + 1;
             }
             if (s64 < ncorr) {
                 s = static_cast<u32>(s64);
                 u32 dense;
-                first_root_dense(s, dense, peak);
+                first_root_dense(s, dist, nblocks, root_list, sc.block_off, dense, peak);
                 const u64 sb = static_cast<u64>(peak) + dist + 1;
                 const u64 sa = static_cast<u64>(row) * (s / row + 1);
-                const u64 sn = max(sa, sb);
-                if (sn < ncorr) nxt = sb >= sa ? nr + dense : static_cast<u32>(sa / row);
-            } else {
-                s = 0xFFFFFFFFu;   // this start is never visited
+                if (max(sa, sb) < ncorr) nxt = sb >= sa ? nr + dense : static_cast<u32>(sa / row);
             }
         }
         sc.cand_s[c] = s;
         sc.cand_peak[c] = peak;
-        sc.ja[c] = (c < ncand && s != 0xFFFFFFFFu) ? nxt : END;
+        sc.ja[c] = nxt;
     }
-    // ---- 3. the first start, from the seed (decode.rs:208-209) ----
+    if (!last_cta_arrives(sc.ticket)) return;
+
+    // ================= last CTA: orbit by pointer doubling =================
+    // ---- the first start, from the seed (decode.rs:208-209) ----
     if (tid == 0) {
         const u32 seed = result->seed_index;
         u32 p1 = 0, start = END;
         u64 s2 = 2ull * row;
         if (seed != kNoSeed) {
             u32 dense;
-            first_root_dense(seed, dense, p1);
+            first_root_dense(seed, dist, nblocks, root_list, sc.block_off, dense, p1);
             const u64 sb = static_cast<u64>(p1) + dist + 1;
             if (sb >= s2) { s2 = sb; start = nr + dense; }
         }
         if (s2 < ncorr) { if (start == END) start = static_cast<u32>(s2 / row); } else start = END;
         positions[0] = p1;
         sc.orbit[0] = start;
-        s_misc[1] = start;
     }
+    // jump tables: shared memory when both fit, else the global ping-pong buffers
+    const bool in_smem = 2ull * (ncand + 1) <= smem_words;
+    u32 *jc = in_smem ? s_tab : sc.ja;
+    u32 *jn = in_smem ? s_tab + (ncand + 1) : sc.jb;
+    if (in_smem)
+        for (u32 i = tid; i <= ncand; i += T) jc[i] = __ldcg(sc.ja + i);
     __syncthreads();
 
-    // ---- 4. pointer doubling; orbit[n + 2^k] = J_k[orbit[n]] ----
-    u32 *jc = sc.ja, *jn = sc.jb;
     const u32 max_events = min(nr + 1, max_positions);   // every event lands in a new row
     for (u32 span = 1; span < max_events; span <<= 1) {
         for (u32 n = tid; n < span && n + span < max_events; n += T) sc.orbit[n + span] = jc[sc.orbit[n]];
@@ -349,19 +367,18 @@ k_pick_parallel(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__
             for (u32 c0 = tid; c0 <= ncand; c0 += 8 * T) {
                 u32 a[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { const u32 c = c0 + i * T; a[i] = c <= ncand ? jc[c] : END; }
+                for (int i = 0; i < 8; ++i) { const u32 ci = c0 + i * T; a[i] = ci <= ncand ? jc[ci] : END; }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) a[i] = jc[a[i]];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { const u32 c = c0 + i * T; if (c <= ncand) jn[c] = a[i]; }
+                for (int i = 0; i < 8; ++i) { const u32 ci = c0 + i * T; if (ci <= ncand) jn[ci] = a[i]; }
             }
         }
         __syncthreads();
         u32 *t = jc; jc = jn; jn = t;
     }
 
-    // ---- 5. events -> positions (decode.rs:241-253) ----
-    // END is absorbing, so the events are the prefix of orbit[] that is != END.
+    // ---- events -> positions (decode.rs:241-253); END is absorbing so events are a prefix of orbit[] ----
     u32 my_events = 0;
     for (u32 n = tid; n < max_events; n += T) {
         const u32 v = sc.orbit[n];
@@ -378,10 +395,9 @@ k_pick_parallel(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__
     __syncthreads();
     const u32 nev = s_misc[2];
     const u32 npeaks = nev == 0 ? 1u : sc.cand_s[sc.orbit[nev - 1]] / row;
-    __syncthreads();   // positions[] complete (written by this CTA) before the row count below
-    __threadfence_block();
+    __syncthreads();
 
-    // ---- 6. rows that fit (decode.rs:125-127): positions are non-decreasing -> count of the passing prefix ----
+    // ---- rows that fit (decode.rs:125-127): positions are non-decreasing -> count of the passing prefix ----
     u32 cnt = 0;
     for (u32 i = tid; i + 1 < npeaks; i += T)
         if (static_cast<u64>(positions[i]) + row < nwork) ++cnt;

@@ -21,11 +21,12 @@ inline unsigned grid_for(u64 n, unsigned per_block, int sms) {
 
 template <int CHUNK>
 int roots_with_chunk(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32 nblocks, u32 *root_list,
-                     u32 *root_count, SyncResult *result) {
+                     u32 *root_count, SyncResult *result, const PickScratch *sc) {
     const size_t smem = 2ull * dist * sizeof(float);
     auto kern = k_roots<1024, CHUNK>;
     APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<nblocks, 1024, smem, c.stream>>>(corr, ncorr, dist, root_list, root_count, result);
+    kern<<<nblocks, 1024, smem, c.stream>>>(corr, ncorr, dist, root_list, root_count, result,
+                                            sc ? sc->block_off : nullptr, sc ? sc->ticket : nullptr);
     APT_CUDA(cudaGetLastError());
     return APT_OK;
 }
@@ -52,21 +53,22 @@ int launch_polyphase(const LaunchCtx &c, const void *signal, int format, u64 len
 int launch_polyphase_tiled(const LaunchCtx &c, const float *signal, u64 len, const float *raw_taps,
                            const float *tile_taps, const u32 *group_xs, const TilePlan &tp, u64 nout, bool envelope,
                            float cosphi2, float sinphi, float *out) {
+    (void)raw_taps;
     if (nout == 0) return APT_OK;
     const u64 tile_out = static_cast<u64>(tp.qt) * tp.p_out;
     const u64 ntiles = (nout + tile_out - 1) / tile_out;
-    const unsigned grid = static_cast<unsigned>(std::min<u64>(ntiles, static_cast<u64>(c.sm_count) * 2));
+    const unsigned grid = static_cast<unsigned>(std::min<u64>(ntiles, static_cast<u64>(c.sm_count) * tp.ctas_per_sm));
     const unsigned block = 32 * tp.groups;
     if (envelope) {
         auto kern = k_polyphase_tiled_f32<true>;
         APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem_bytes)));
-        kern<<<grid, block, tp.smem_bytes, c.stream>>>(signal, len, raw_taps, tile_taps, group_xs, tp, nout, ntiles,
-                                                        cosphi2, sinphi, out);
+        kern<<<grid, block, tp.smem_bytes, c.stream>>>(signal, len, tile_taps, group_xs, tp, nout, ntiles, cosphi2,
+                                                        sinphi, out);
     } else {
         auto kern = k_polyphase_tiled_f32<false>;
         APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem_bytes)));
-        kern<<<grid, block, tp.smem_bytes, c.stream>>>(signal, len, raw_taps, tile_taps, group_xs, tp, nout, ntiles,
-                                                        cosphi2, sinphi, out);
+        kern<<<grid, block, tp.smem_bytes, c.stream>>>(signal, len, tile_taps, group_xs, tp, nout, ntiles, cosphi2,
+                                                        sinphi, out);
     }
     APT_CUDA(cudaGetLastError());
     return APT_OK;
@@ -99,25 +101,31 @@ int launch_corr(const LaunchCtx &c, const float *f, u64 ncorr, const int8_t *gua
 }
 
 int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32 *root_list, u32 *root_count,
-                 SyncResult *result) {
+                 SyncResult *result, const PickScratch *sc) {
     const u32 nblocks = static_cast<u32>((ncorr + dist - 1) / dist);
     const u32 need = (dist + 1023) / 1024;
-    if (need <= 5) return roots_with_chunk<5>(c, corr, ncorr, dist, nblocks, root_list, root_count, result);
-    if (need <= 7) return roots_with_chunk<7>(c, corr, ncorr, dist, nblocks, root_list, root_count, result);
-    if (need <= 9) return roots_with_chunk<9>(c, corr, ncorr, dist, nblocks, root_list, root_count, result);
-    if (need <= 16) return roots_with_chunk<16>(c, corr, ncorr, dist, nblocks, root_list, root_count, result);
+    if (need <= 5) return roots_with_chunk<5>(c, corr, ncorr, dist, nblocks, root_list, root_count, result, sc);
+    if (need <= 7) return roots_with_chunk<7>(c, corr, ncorr, dist, nblocks, root_list, root_count, result, sc);
+    if (need <= 9) return roots_with_chunk<9>(c, corr, ncorr, dist, nblocks, root_list, root_count, result, sc);
+    if (need <= 16) return roots_with_chunk<16>(c, corr, ncorr, dist, nblocks, root_list, root_count, result, sc);
     return fail(APT_ERR_BAD_ARG, "work rate too high for the sync picker (min_distance %u)", dist);
 }
 
 int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *root_list,
                 const u32 *root_count, u32 nblocks, u32 *positions, u32 max_positions, SyncResult *result,
                 const PickScratch *scratch) {
-    if (scratch)
-        k_pick_parallel<<<1, 1024, 0, c.stream>>>(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions,
-                                                  max_positions, result, *scratch);
-    else
+    if (scratch) {
+        // one thread per candidate; the last CTA to finish walks the orbit with its jump tables in shared memory
+        constexpr size_t kSmem = 200 * 1024;
+        // (per device, cheap: not cached so that every GPU of a batch gets it)
+        APT_CUDA(cudaFuncSetAttribute(k_pick_links, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
+        const unsigned grid = (scratch->cap + 1 + 1023) / 1024;
+        k_pick_links<<<grid, 1024, kSmem, c.stream>>>(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions,
+                                                      max_positions, result, *scratch, static_cast<u32>(kSmem / 4));
+    } else {
         k_pick_sequential<<<1, 32, 0, c.stream>>>(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions,
                                                   max_positions, result);
+    }
     APT_CUDA(cudaGetLastError());
     return APT_OK;
 }
@@ -125,8 +133,8 @@ int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, con
 static size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
 size_t pick_scratch_bytes(u32 max_blocks, u32 max_positions, u32 cap) {
-    return 2 * align_up((static_cast<size_t>(max_blocks) + 1) * 4) + 4 * align_up((static_cast<size_t>(cap) + 1) * 4) +
-           align_up((static_cast<size_t>(max_positions) + 1) * 4);
+    return align_up((static_cast<size_t>(max_blocks) + 1) * 4) + 4 * align_up((static_cast<size_t>(cap) + 1) * 4) +
+           align_up((static_cast<size_t>(max_positions) + 1) * 4) + align_up(8);
 }
 
 PickScratch pick_scratch_carve(void *base, u32 max_blocks, u32 max_positions, u32 cap) {
@@ -138,12 +146,12 @@ PickScratch pick_scratch_carve(void *base, u32 max_blocks, u32 max_positions, u3
     };
     PickScratch s;
     s.block_off = take(static_cast<size_t>(max_blocks) + 1);
-    s.next_ne = take(static_cast<size_t>(max_blocks) + 1);
     s.cand_s = take(static_cast<size_t>(cap) + 1);
     s.cand_peak = take(static_cast<size_t>(cap) + 1);
     s.ja = take(static_cast<size_t>(cap) + 1);
     s.jb = take(static_cast<size_t>(cap) + 1);
     s.orbit = take(static_cast<size_t>(max_positions) + 1);
+    s.ticket = take(2);
     s.cap = cap;
     return s;
 }

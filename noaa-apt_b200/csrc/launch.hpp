@@ -25,25 +25,34 @@ struct SyncResult {
 
 // Global scratch of the parallel peak picker (k_pick_parallel).
 struct PickScratch {
-    u32 *block_off;    // [nblocks + 1] exclusive scan of root_count
-    u32 *next_ne;      // [nblocks + 1] smallest non-empty block >= b (nblocks if none)
+    u32 *block_off;    // [nblocks + 1] exclusive scan of root_count (dense root numbering)
     u32 *cand_s;       // [cap + 1] start position of each candidate
     u32 *cand_peak;    // [cap + 1] firstroot(start)
-    u32 *ja, *jb;      // [cap + 1] ping-pong jump tables
+    u32 *ja, *jb;      // [cap + 1] jump tables (J0, and the global ping-pong pair when smem is too small)
     u32 *orbit;        // [max_positions + 1]
+    u32 *ticket;       // [2] last-CTA tickets of k_roots / k_pick_links (zero between launches)
     u32 cap;           // candidate capacity
 };
 
-// Geometry of the tiled kernel for one (L, M, taps) triple; built on the host (see make_tile_plan).
+// Geometry of the tiled kernel for one (L, M, taps) triple; built on the host (make_tile_plan).
 struct TilePlan {
     u32 l, m;          // resampling ratio
-    u32 groups;        // G = L / gcd(R, L)  (= warps per CTA)
-    u32 p_out, p_in;   // outputs / inputs per super-period
-    u32 usteps;        // U: padded taps per output group (multiple of 4*KS)
-    u32 row_len;       // floats per shared-memory row: >= p_in + usteps, multiple of 4, row_len/4 odd
+    u32 groups;        // G = L / gcd(8, L)  (= warps per CTA); group g owns outputs 8g..8g+7 of a super-period
+    u32 p_out, p_in;   // outputs / inputs per super-period (p_out = 8G)
+    u32 usteps;        // samples a group reads per row (= half_taps + shift), multiple of 16
+    u32 half_taps;     // padded taps of one half (4 outputs), multiple of 16
+    u32 shift;         // half B's window starts this many samples after half A's (multiple of 16)
+    u32 iters;         // loop iterations = usteps / 16
+    u32 row_len;       // floats per shared-memory row: multiple of 4, row_len/4 odd
+    u32 rows_floats;   // floats of the row buffer (also holds the partial-sum planes)
+    u32 plane_pitch;   // floats per row of a partial-sum plane (p_out + 4)
     u32 qt;            // rows (super-periods) per tile
+    u32 slice_stride;  // floats per (iteration, slice lane) tap record: 16 A + 16 B + 4 pad
+    u32 group_stride;  // floats of one group's tap table
     u32 smem_bytes;    // dynamic shared memory
-    u64 off2;          // 2*((N-1)/2), for the halo output computed from the raw taps
+    u32 ctas_per_sm;   // 2 when two CTAs fit an SM, else 1
+    u64 off2;          // 2*((N-1)/2)
+    u32 debug;         // 0 normal; 1 skip the FMA loop; 2 skip the loads (timing experiments only)
 };
 
 struct LaunchCtx {
@@ -64,7 +73,7 @@ int launch_envelope(const LaunchCtx &c, const float *x, u64 n, float cosphi2, fl
 int launch_corr(const LaunchCtx &c, const float *f, u64 ncorr, const int8_t *guard, u32 glen, float *corr);
 // roots of the correlation (see kernels_sync.cuh).
 int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32 *root_list, u32 *root_count,
-                 SyncResult *result);
+                 SyncResult *result, const PickScratch *scratch /* nullptr: no dense numbering */);
 // orbit walk -> sync positions (decode.rs:241-253).
 int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *root_list,
                 const u32 *root_count, u32 nblocks, u32 *positions, u32 max_positions, SyncResult *result,

@@ -1,5 +1,6 @@
 // Host-side geometry of the tiled polyphase kernel (kernels_fast.cuh).
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 
 #include "launch.hpp"
@@ -7,9 +8,11 @@
 namespace aptb200 {
 
 namespace {
-constexpr u32 kR = 8, kQ = 4, kKS = 4, kQT = (32 / kKS) * kQ;
-constexpr u32 kMaxGroups = 13;              // warps per CTA the kernel is compiled for (416 threads, 2 CTAs/SM)
-constexpr u32 kSmemTwoCtas = 113 * 1024;    // per-CTA budget that still lets two CTAs share an SM
+constexpr u32 kR = 8, kH = 4, kQ = 4, kKS = 4, kQT = (32 / kKS) * kQ;
+constexpr u32 kMaxGroups = 13;                 // warps per CTA the kernel is compiled for (416 threads)
+constexpr u32 kSmemTwoCtas = (233472 - 2 * 1024) / 2 - 512;   // dynamic bytes that still let two CTAs share an SM
+constexpr u32 kSmemOneCta = 227 * 1024 - 512;
+constexpr u32 kIterSamples = 4 * kKS;          // samples consumed per loop iteration (one 16-byte chunk per slice lane)
 }  // namespace
 
 bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, std::vector<float> &tile_taps,
@@ -19,36 +22,85 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
     const u32 groups = l / std::gcd(kR, l);
     if (groups > kMaxGroups) return false;
     const u64 p_out = static_cast<u64>(kR) * groups;
-    const u64 p_in = p_out * m / l;          // exact: p_out is a multiple of l
+    const u64 p_in = p_out * m / l;            // exact: p_out is a multiple of l
     if (p_in % 4 != 0 || p_in > (1u << 20)) return false;
 
-    group_xs.assign(groups, 0);
-    u64 need = 0, max_xs = 0;
+    // Per group: outputs k0..k0+3 (half A) and k0+4..k0+7 (half B).  Half B's window starts `shift`
+    // samples after half A's, so the first shift/16 loop iterations touch only A and the last only B.
+    auto first_x = [&](u64 k) { return (k * m + l - 1) / l; };          // first sample output k touches
+    auto last_x = [&](u64 k) { return (k * m + off2) / l; };            // last one
+    u64 d_min = ~0ull, d_max = 0;
     for (u32 g = 0; g < groups; ++g) {
         const u64 k0 = static_cast<u64>(kR) * g;
-        const u64 xs = (k0 * m + l - 1) / l;            // first sample output k0 touches
-        const u64 xs4 = xs & ~static_cast<u64>(3);      // 16-byte aligned window start
-        const u64 xmax = ((k0 + kR - 1) * m + off2) / l;   // last sample output k0+R-1 touches
-        group_xs[g] = static_cast<u32>(xs4);
-        need = std::max(need, xmax - xs4 + 1);
-        max_xs = std::max(max_xs, xs4);
+        const u64 d = first_x(k0 + kH) - first_x(k0);
+        d_min = std::min(d_min, d);
+        d_max = std::max(d_max, d);
     }
-    const u64 usteps = (need + 4 * kKS - 1) / (4 * kKS) * (4 * kKS);
-    u64 row_len = (max_xs + usteps + 3) / 4 * 4;
-    row_len = std::max(row_len, (p_in + 3) / 4 * 4);    // the halo output and edge fills index whole periods
-    if ((row_len / 4) % 2 == 0) row_len += 4;           // odd pitch in 16-byte units: conflict-free LDS.128
-    const u64 smem = 16 + groups * usteps * kR * 4 + static_cast<u64>(kQT) * row_len * 4;
-    if (smem > kSmemTwoCtas) return false;
-    if (static_cast<u64>(kQT) * p_out + 1 > static_cast<u64>(kQT) * row_len) return false;   // parked tile must fit
+    // Candidate shifts (multiples of one loop iteration).  A larger shift than the smallest spacing is fine
+    // as long as every group's window start is pulled back far enough for half B to still see its first tap.
+    u64 shift = 0, ua = 0, max_w0 = 0;
+    bool have = false;
+    const u64 cands[3] = {0, d_min / kIterSamples * kIterSamples, (d_max + kIterSamples - 1) / kIterSamples * kIterSamples};
+    for (u64 cand : cands) {
+        std::vector<u32> xs(groups);
+        u64 need = 0, mw = 0;
+        bool ok = true;
+        for (u32 g = 0; g < groups && ok; ++g) {
+            const u64 k0 = static_cast<u64>(kR) * g;
+            if (first_x(k0 + kH) < cand) { ok = false; break; }
+            const u64 w0 = std::min(first_x(k0), first_x(k0 + kH) - cand) & ~static_cast<u64>(3);   // 16-byte aligned
+            xs[g] = static_cast<u32>(w0);
+            need = std::max(need, last_x(k0 + kH - 1) - w0 + 1);               // half A relative to w0
+            need = std::max(need, last_x(k0 + kR - 1) - (w0 + cand) + 1);      // half B relative to w0 + shift
+            mw = std::max(mw, w0);
+        }
+        if (!ok) continue;
+        const u64 cand_ua = (need + kIterSamples - 1) / kIterSamples * kIterSamples;   // taps per half, padded
+        if (!have || cand_ua < ua || (cand_ua == ua && cand_ua + cand < ua + shift)) {
+            have = true;
+            shift = cand;
+            ua = cand_ua;
+            max_w0 = mw;
+            group_xs = xs;
+        }
+    }
+    if (!have) return false;
+    const u64 span = ua + shift;                                              // samples a group reads per row
+    const u64 iters = span / kIterSamples;
+    u64 row_len = (max_w0 + span + 3) / 4 * 4;
+    row_len = std::max(row_len, (p_in + 3) / 4 * 4);
+    if ((row_len / 4) % 2 == 0) row_len += 4;            // odd pitch in 16-byte units: conflict-free LDS.128
 
-    tile_taps.assign(groups * usteps * kR, 0.f);
+    // Tap table [group][iteration][slice lane][36]: 16 floats for half A (4 u x 4 r), 16 for half B, 4 pad --
+    // the pad skews the four slice lanes of a warp onto different 16-byte bank groups.
+    const u64 lane_stride = 2 * 4 * kH + 4;
+    const u64 group_stride = iters * kKS * lane_stride;
+    const u64 plane_pitch = p_out + 4;                   // partial-sum planes [slice][row][p_out + 4]
+    u64 rows_floats = static_cast<u64>(kQT) * row_len;
+    rows_floats = std::max(rows_floats, kKS * static_cast<u64>(kQT) * plane_pitch);   // planes alias the rows
+    const u64 smem = 16 + groups * group_stride * 4 + rows_floats * 4 + span * 4;
+    if (smem > kSmemOneCta) return false;
+    if ((plane_pitch / 4) % 2 == 0) return false;        // p_out/4 must be even (8 | p_out): always true
+
+    tile_taps.assign(groups * group_stride, 0.f);
+    auto tap_at = [&](long long idx) -> float {
+        return idx >= 0 && static_cast<u64>(idx) <= off2 ? taps[static_cast<size_t>(idx)] : 0.f;
+    };
     for (u32 g = 0; g < groups; ++g) {
-        for (u64 u = 0; u < usteps; ++u) {
-            for (u32 r = 0; r < kR; ++r) {
-                const long long idx = static_cast<long long>((group_xs[g] + u) * l) -
-                                      static_cast<long long>((static_cast<u64>(kR) * g + r) * m);
-                if (idx >= 0 && static_cast<u64>(idx) <= off2)
-                    tile_taps[(static_cast<size_t>(g) * usteps + u) * kR + r] = taps[static_cast<size_t>(idx)];
+        const u64 k0 = static_cast<u64>(kR) * g;
+        for (u64 it = 0; it < iters; ++it) {
+            for (u32 ks = 0; ks < kKS; ++ks) {
+                float *dst = &tile_taps[g * group_stride + (it * kKS + ks) * lane_stride];
+                for (u32 uu = 0; uu < 4; ++uu) {
+                    const u64 u = (it * kKS + ks) * 4 + uu;             // sample index relative to w0
+                    const long long x = static_cast<long long>(group_xs[g] + u);
+                    for (u32 r = 0; r < kH; ++r) {
+                        // half A sees sample u as its tap u; half B (window starts `shift` later) likewise
+                        dst[uu * kH + r] = u < ua ? tap_at(x * l - static_cast<long long>((k0 + r) * m)) : 0.f;
+                        dst[16 + uu * kH + r] =
+                            u >= shift ? tap_at(x * l - static_cast<long long>((k0 + kH + r) * m)) : 0.f;
+                    }
+                }
             }
         }
     }
@@ -57,11 +109,21 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
     tp.groups = groups;
     tp.p_out = static_cast<u32>(p_out);
     tp.p_in = static_cast<u32>(p_in);
-    tp.usteps = static_cast<u32>(usteps);
+    tp.usteps = static_cast<u32>(span);
+    tp.half_taps = static_cast<u32>(ua);
+    tp.shift = static_cast<u32>(shift);
+    tp.iters = static_cast<u32>(iters);
     tp.row_len = static_cast<u32>(row_len);
+    tp.rows_floats = static_cast<u32>(rows_floats);
+    tp.plane_pitch = static_cast<u32>(plane_pitch);
     tp.qt = kQT;
+    tp.slice_stride = static_cast<u32>(lane_stride);
+    tp.group_stride = static_cast<u32>(group_stride);
     tp.smem_bytes = static_cast<u32>(smem);
+    tp.ctas_per_sm = smem <= kSmemTwoCtas ? 2 : 1;
     tp.off2 = off2;
+    tp.debug = 0;
+    if (const char *e = getenv("APTB200_TILE_DEBUG")) tp.debug = static_cast<u32>(atoi(e));
     return true;
 }
 

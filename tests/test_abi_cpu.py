@@ -139,3 +139,61 @@ def test_profiles(na):
     s = na.Settings.profile("slow")
     assert (s.work_rate, s.resample_atten, s.resample_delta_freq) == (20800, 40.0, 500.0)
     assert na.Settings.profile("standard") == na.Settings()
+
+
+def _tile_plan(na, l, m, taps):
+    """(info, tapsA[g][u][4], tapsB[g][u][4], w0[g]) with u relative to w0 (A) -- B's u also relative to w0."""
+    lib = na._lib.load()
+    info = na._lib.CTileInfo()
+    assert lib.apt_tile_plan(l, m, taps.ctypes.data, taps.size, C.byref(info), None, 0, None, 0) == 0
+    if not info.usable:
+        return None, None, None, None
+    tt = np.zeros(info.groups * info.group_stride, np.float32)
+    xs = np.zeros(info.groups, np.uint32)
+    assert lib.apt_tile_plan(l, m, taps.ctypes.data, taps.size, C.byref(info), tt.ctypes.data, tt.size,
+                             xs.ctypes.data, xs.size) == 0
+    rec = tt.reshape(info.groups, info.iters * info.slices, info.slice_stride)      # [g][chunk][36]
+    ta = rec[:, :, 0:16].reshape(info.groups, info.usteps, 4)                      # [g][u][r]
+    tb = rec[:, :, 16:32].reshape(info.groups, info.usteps, 4)
+    return info, ta, tb, xs
+
+
+@pytest.mark.parametrize("rate,work,l,m", [(48000, 12480, 13, 50), (96000, 12480, 13, 100), (48000, 20800, 13, 30),
+                                           (48000, 16640, 26, 75)])
+def test_tile_plan_geometry_reproduces_fast_resampling(na, rate, work, l, m):
+    """The tiled kernel's host-built geometry (groups, window starts, the two half windows, zero-padded tap
+    records), emulated with numpy, must give fast_resampling's outputs (dsp.rs:186-289) -- vs the oracle."""
+    import math
+    import oracle
+    f = na.filters.LowpassDcRemoval(na.Freq.hz(4800, rate), 30.0, na.Freq.hz(1000, rate))
+    f.resample(rate, rate * l)
+    h = f.design()
+    info, ta, tb, xs = _tile_plan(na, l, m, h)
+    assert info is not None and info.usable
+    assert info.p_out * m == info.p_in * l and info.p_in % 4 == 0 and info.p_out == 8 * info.groups
+    assert (info.row_len // 4) % 2 == 1 and (info.slice_stride // 4) % 2 == 1      # bank-group skews
+    assert info.usteps == info.half_taps + info.shift == 16 * info.iters and info.shift % 16 == 0
+    assert all(int(v) % 4 == 0 and int(v) + info.usteps <= info.row_len for v in xs)
+    assert info.ctas_per_sm * (info.smem_bytes + 1024 + 512) <= 228 * 1024
+    # the loop skips half B before `shift` and half A after `half_taps`: those taps must be zero
+    assert not tb[:, : info.shift].any() and not ta[:, info.half_taps:].any()
+    x = (np.random.default_rng(0).standard_normal(30000) * 1000).astype(np.float32)
+    ref = oracle.fast_resampling(x, l, m, h)
+    qt, tile_out = info.rows_per_tile, info.rows_per_tile * info.p_out
+    xpad = np.concatenate([x.astype(np.float64), np.zeros(qt * info.p_in + info.row_len + 16)])
+    out = np.zeros(ref.size + tile_out)
+    for t in range(math.ceil(ref.size / tile_out)):
+        xb = t * qt * info.p_in
+        for q in range(qt):
+            for g in range(info.groups):
+                win = xpad[xb + q * info.p_in + int(xs[g]): xb + q * info.p_in + int(xs[g]) + info.usteps]
+                k = t * tile_out + q * info.p_out + 8 * g
+                out[k:k + 4] = win @ ta[g].astype(np.float64)
+                out[k + 4:k + 8] = win @ tb[g].astype(np.float64)
+    assert np.max(np.abs(out[:ref.size] - ref)) <= 1e-6 * np.max(np.abs(ref))
+
+
+def test_tile_plan_rejects_shapes_it_cannot_hold(na):
+    h = np.ones(14057, np.float32)
+    info, _, _, _ = _tile_plan(na, 832, 735, h)          # 11025 Hz: 208 groups > 13 warps -> generic kernel
+    assert info is None

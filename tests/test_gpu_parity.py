@@ -189,7 +189,8 @@ def test_decode_pcm16_equals_f32():
     pcm = synth.apt_pcm16(rate, 12, seed=5)
     a = na.decode(na.Context(), na.Settings(), pcm, rate, True)
     b = na.decode(na.Context(), na.Settings(), pcm.astype(np.float32), rate, True)
-    assert np.array_equal(a, b)
+    # the PCM16 and f32 loads may run different kernels (different summation order), same tolerance
+    assert a.size == b.size and nerr(a, b) <= TOL
 
 
 def test_decode_no_sync():
