@@ -69,19 +69,41 @@ constexpr int kTileR = 8, kTileH = 4, kTileQ = 4, kTileKS = 4;
 constexpr int kTileRowLanes = 32 / kTileKS;           // 8
 constexpr int kTileQT = kTileRowLanes * kTileQ;       // 32 rows per tile
 
-// one half (4 outputs) x 4 rows x 4 consecutive samples
-__device__ __forceinline__ void half_fma(float (&acc)[kTileH][kTileQ], const float4 *__restrict__ t,
-                                         const float4 (&s)[kTileQ]) {
+// ---- packed fp32x2 helpers: one FFMA2 issue slot does two FMAs (each half rounded on its own) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float4 lds128(u32 addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// One half (4 outputs, as two packed pairs) x 4 rows x the 4 consecutive samples of one 16-byte chunk.
+// acc[p][j] packs outputs (2p, 2p+1) of row j; the tap pair comes straight out of the LDS.128 register quad,
+// the sample is duplicated into both lanes of the packed operand.
+__device__ __forceinline__ void half_fma2(f32x2 (&acc)[2][kTileQ], u32 tap_addr, const float4 (&s)[kTileQ]) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const float4 tp = t[u];                      // taps of outputs r = 0..3 for sample u of the chunk
+        const float4 tp = lds128(tap_addr + 16 * u);  // taps of outputs r = 0..3 for sample u of the chunk
+        const f32x2 t01 = pack2(tp.x, tp.y), t23 = pack2(tp.z, tp.w);
 #pragma unroll
         for (int j = 0; j < kTileQ; ++j) {
             const float sv = u == 0 ? s[j].x : u == 1 ? s[j].y : u == 2 ? s[j].z : s[j].w;
-            acc[0][j] = fmaf(tp.x, sv, acc[0][j]);
-            acc[1][j] = fmaf(tp.y, sv, acc[1][j]);
-            acc[2][j] = fmaf(tp.z, sv, acc[2][j]);
-            acc[3][j] = fmaf(tp.w, sv, acc[3][j]);
+            const f32x2 sv2 = pack2(sv, sv);
+            acc[0][j] = fma2(t01, sv2, acc[0][j]);
+            acc[1][j] = fma2(t23, sv2, acc[1][j]);
         }
     }
 }
@@ -150,16 +172,25 @@ k_polyphase_tiled_f32(const float *__restrict__ signal, u64 len, const float *__
             if (lane == 0) {
                 fence_proxy_async();
                 for (u32 q = warp; q < QT; q += tp.groups) {
+                    if (tp.debug >= 3) {   // timing experiment: 128-byte aligned source (wrong data)
+                        const u64 xa = (x_base + static_cast<u64>(q) * tp.p_in) & ~static_cast<u64>(31);
+                        tma_bulk_g2s(s_rows + q * tp.row_len, signal + xa, tp.row_len * 4, bar);
+                    } else
                     tma_bulk_g2s(s_rows + q * tp.row_len, signal + x_base + static_cast<u64>(q) * tp.p_in,
                                  tp.row_len * 4, bar);
-                    // pull the same row of this CTA's next tile into L2 while this one is being computed
-                    const u64 nx = x_base + (static_cast<u64>(gridDim.x) * QT + q) * tp.p_in;
-                    if (tile + gridDim.x < ntiles && nx + tp.p_in <= len) tma_prefetch_l2(signal + nx, tp.p_in * 4);
                 }
                 if (want_halo && warp == tp.groups - 1) tma_bulk_g2s(s_vrow, signal + x_halo, tp.usteps * 4, bar);
             }
             mbar_wait(bar, phase);
             phase ^= 1;
+            // this tile has landed: pull the rows of this CTA's next tile into L2 while we compute, so that
+            // HBM stays busy during the FMA phase (CTAs run in lockstep; without this loads and math alternate)
+            if (lane == 0 && tile + gridDim.x < ntiles) {
+                for (u32 q = warp; q < QT; q += tp.groups) {
+                    const u64 nx = x_base + (static_cast<u64>(gridDim.x) * QT + q) * tp.p_in;
+                    if (nx + tp.p_in <= len) tma_prefetch_l2(signal + nx, tp.p_in * 4);
+                }
+            }
         } else {
             for (u32 i = tid; i < QT * tp.row_len; i += nthreads) {
                 const u32 q = i / tp.row_len, c = i - q * tp.row_len;
@@ -171,8 +202,64 @@ k_polyphase_tiled_f32(const float *__restrict__ signal, u64 len, const float *__
             __syncthreads();
         }
 
+        // ---- the product: 8 x 4 accumulators per thread (16 packed pairs) over this lane's chunks ----
+        f32x2 acc_a[2][Q], acc_b[2][Q];
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int j = 0; j < Q; ++j) acc_a[p][j] = acc_b[p][j] = 0ull;
+        if (tp.debug != 1 && tp.debug != 3) {
+            // 32-bit shared-memory byte addresses, advanced by constants: no per-iteration address math
+            u32 tap_addr = smem_u32(s_taps) + (warp * tp.group_stride + ks * tp.slice_stride) * 4;
+            const u32 tap_step = KS * tp.slice_stride * 4;
+            u32 row_addr = smem_u32(s_rows) + (ql * tp.row_len + w0 + ks * 4) * 4;
+            const u32 row_step8 = 8 * tp.row_len * 4;            // rows ql, ql+8, ql+16, ql+24
+            u32 it = 0;
+            for (; it < it_b_begin; ++it) {                        // half A only
+                float4 s[Q];
+#pragma unroll
+                for (int j = 0; j < Q; ++j) s[j] = lds128(row_addr + j * row_step8);
+                half_fma2(acc_a, tap_addr, s);
+                row_addr += KS * 16;
+                tap_addr += tap_step;
+            }
+            for (; it < it_a_end; ++it) {                          // both halves
+                float4 s[Q];
+#pragma unroll
+                for (int j = 0; j < Q; ++j) s[j] = lds128(row_addr + j * row_step8);
+                half_fma2(acc_a, tap_addr, s);
+                half_fma2(acc_b, tap_addr + 64, s);
+                row_addr += KS * 16;
+                tap_addr += tap_step;
+            }
+            for (; it < tp.iters; ++it) {                          // half B only
+                float4 s[Q];
+#pragma unroll
+                for (int j = 0; j < Q; ++j) s[j] = lds128(row_addr + j * row_step8);
+                half_fma2(acc_b, tap_addr + 64, s);
+                row_addr += KS * 16;
+                tap_addr += tap_step;
+            }
+        }
+        __syncthreads();   // every warp is done reading the rows: the buffer now takes the partial sums
+
+        // ---- partial sums of the 4 slices -> planes [ks][row][plane_pitch] ----
+        float *s_plane = s_rows;
+        const u32 plane_floats = QT * tp.plane_pitch;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            float *dst = s_plane + ks * plane_floats + (ql + 8 * j) * tp.plane_pitch + warp * kTileR;
+            float4 va, vb;
+            unpack2(acc_a[0][j], va.x, va.y);
+            unpack2(acc_a[1][j], va.z, va.w);
+            unpack2(acc_b[0][j], vb.x, vb.y);
+            unpack2(acc_b[1][j], vb.z, vb.w);
+            *reinterpret_cast<float4 *>(dst) = va;
+            *reinterpret_cast<float4 *>(dst + 4) = vb;
+        }
+        __syncthreads();
         // ---- r[K0 - 1]: output 7 of the last group of the previous super-period, from the virtual row ----
-        if (ENVELOPE && warp == 0) {
+        if (ENVELOPE && warp == tp.groups - 1) {
             float part = 0.f;
             if (want_halo) {
                 const float *tg = s_taps + static_cast<size_t>(tp.groups - 1) * tp.group_stride;
@@ -186,89 +273,43 @@ k_polyphase_tiled_f32(const float *__restrict__ signal, u64 len, const float *__
             if (lane == 0) s_halo = part;
         }
 
-        // ---- the product: 8 x 4 accumulators per thread over this lane's chunks ----
-        float acc_a[H][Q], acc_b[H][Q];
-#pragma unroll
-        for (int r = 0; r < H; ++r)
-#pragma unroll
-            for (int j = 0; j < Q; ++j) acc_a[r][j] = acc_b[r][j] = 0.f;
-        if (tp.debug != 1) {
-            const float4 *tap4 = reinterpret_cast<const float4 *>(s_taps + static_cast<size_t>(warp) * tp.group_stride +
-                                                                  ks * tp.slice_stride);
-            const u32 tap_it = KS * tp.slice_stride / 4;           // float4 per iteration
-            const float4 *rp[Q];
-#pragma unroll
-            for (int j = 0; j < Q; ++j)
-                rp[j] = reinterpret_cast<const float4 *>(s_rows + (ql + 8 * j) * tp.row_len + w0) + ks;
-            u32 it = 0;
-            for (; it < it_b_begin; ++it) {                        // half A only
-                float4 s[Q];
-#pragma unroll
-                for (int j = 0; j < Q; ++j) s[j] = rp[j][it * KS];
-                half_fma(acc_a, tap4 + it * tap_it, s);
-            }
-            for (; it < it_a_end; ++it) {                          // both halves
-                float4 s[Q];
-#pragma unroll
-                for (int j = 0; j < Q; ++j) s[j] = rp[j][it * KS];
-                half_fma(acc_a, tap4 + it * tap_it, s);
-                half_fma(acc_b, tap4 + it * tap_it + 4, s);
-            }
-            for (; it < tp.iters; ++it) {                          // half B only
-                float4 s[Q];
-#pragma unroll
-                for (int j = 0; j < Q; ++j) s[j] = rp[j][it * KS];
-                half_fma(acc_b, tap4 + it * tap_it + 4, s);
-            }
-        }
-        __syncthreads();   // every warp is done reading the rows: the buffer now takes the partial sums
-
-        // ---- partial sums of the 4 slices -> planes [ks][row][plane_pitch] ----
-        float *s_plane = s_rows;
-        const u32 plane_floats = QT * tp.plane_pitch;
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            float *dst = s_plane + ks * plane_floats + (ql + 8 * j) * tp.plane_pitch + warp * kTileR;
-            *reinterpret_cast<float4 *>(dst) = make_float4(acc_a[0][j], acc_a[1][j], acc_a[2][j], acc_a[3][j]);
-            *reinterpret_cast<float4 *>(dst + 4) = make_float4(acc_b[0][j], acc_b[1][j], acc_b[2][j], acc_b[3][j]);
-        }
-        __syncthreads();
         // ---- reduce the planes into plane 0 (4 outputs per thread-iteration) ----
         const u32 vec_per_row = tp.p_out / 4;
         const u32 nvec = QT * vec_per_row;
         for (u32 v = tid; v < nvec; v += nthreads) {
-            const u32 q = v / vec_per_row, c4 = v - q * vec_per_row;
-            float4 *p0 = reinterpret_cast<float4 *>(s_plane + q * tp.plane_pitch) + c4;
-            const float4 a = *p0;
-            const float4 b = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p0) + plane_floats);
-            const float4 c = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p0) + 2 * plane_floats);
-            const float4 d = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p0) + 3 * plane_floats);
-            *p0 = make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z),
-                              (a.w + b.w) + (c.w + d.w));
+            const u32 q = (v * tp.vec_magic) >> 16, c4 = v - q * vec_per_row;      // v / vec_per_row, exact for v < nvec
+            float *p0 = s_plane + q * tp.plane_pitch + 4 * c4;
+            const float4 a = *reinterpret_cast<const float4 *>(p0);
+            const float4 b = *reinterpret_cast<const float4 *>(p0 + plane_floats);
+            const float4 c = *reinterpret_cast<const float4 *>(p0 + 2 * plane_floats);
+            const float4 d = *reinterpret_cast<const float4 *>(p0 + 3 * plane_floats);
+            *reinterpret_cast<float4 *>(p0) = make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y),
+                                                          (a.z + b.z) + (c.z + d.z), (a.w + b.w) + (c.w + d.w));
         }
         __syncthreads();
         // ---- epilogue: envelope (dsp.rs:373) and 16-byte stores ----
+        const bool full_tile = k_base + tile_out <= nout && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+        float *out_tile = out + k_base;
         for (u32 v = tid; v < nvec; v += nthreads) {
-            const u32 q = v / vec_per_row, c4 = v - q * vec_per_row;
-            const u64 k = k_base + static_cast<u64>(q) * tp.p_out + 4 * c4;
-            if (k >= nout) continue;
-            const float *row = s_plane + q * tp.plane_pitch;
-            const float4 cur = *reinterpret_cast<const float4 *>(row + 4 * c4);
+            const u32 q = (v * tp.vec_magic) >> 16, c4 = v - q * vec_per_row;
+            const u32 kl = q * tp.p_out + 4 * c4;                    // output index inside the tile
+            const float *cell = s_plane + q * tp.plane_pitch + 4 * c4;
+            const float4 cur = *reinterpret_cast<const float4 *>(cell);
             float4 res = cur;
             if (ENVELOPE) {
-                float prev;
-                if (c4 > 0) prev = row[4 * c4 - 1];
-                else if (q > 0) prev = row[-static_cast<int>(tp.plane_pitch) + static_cast<int>(tp.p_out) - 1];
-                else prev = s_halo;
-                res.x = k == 0 ? 0.f : envelope2_fast(prev, cur.x, cosphi2, inv_sinphi);
+                // previous output: left neighbour, last output of the previous row, or the halo for kl == 0
+                const float prev = c4 > 0 ? cell[-1] : q > 0 ? cell[-5] : s_halo;
+                res.x = envelope2_fast(prev, cur.x, cosphi2, inv_sinphi);
                 res.y = envelope2_fast(cur.x, cur.y, cosphi2, inv_sinphi);
                 res.z = envelope2_fast(cur.y, cur.z, cosphi2, inv_sinphi);
                 res.w = envelope2_fast(cur.z, cur.w, cosphi2, inv_sinphi);
+                if (kl == 0 && k_base == 0) res.x = 0.f;             // output[0] = 0 (dsp.rs:357)
             }
-            if (k + 4 <= nout && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-                *reinterpret_cast<float4 *>(out + k) = res;
+            if (full_tile) {
+                *reinterpret_cast<float4 *>(out_tile + kl) = res;
             } else {
-                out[k] = res.x;
+                const u64 k = k_base + kl;
+                if (k < nout) out[k] = res.x;
                 if (k + 1 < nout) out[k + 1] = res.y;
                 if (k + 2 < nout) out[k + 2] = res.z;
                 if (k + 3 < nout) out[k + 3] = res.w;

@@ -46,6 +46,7 @@ struct TilePlan {
     u32 row_len;       // floats per shared-memory row: multiple of 4, row_len/4 odd
     u32 rows_floats;   // floats of the row buffer (also holds the partial-sum planes)
     u32 plane_pitch;   // floats per row of a partial-sum plane (p_out + 4)
+    u32 vec_magic;     // (v * vec_magic) >> 16 == v / (p_out/4) for every v < qt*p_out/4
     u32 qt;            // rows (super-periods) per tile
     u32 slice_stride;  // floats per (iteration, slice lane) tap record: 16 A + 16 B + 4 pad
     u32 group_stride;  // floats of one group's tap table

@@ -117,6 +117,12 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
     tp.rows_floats = static_cast<u32>(rows_floats);
     tp.plane_pitch = static_cast<u32>(plane_pitch);
     tp.qt = kQT;
+    {
+        const u32 vpr = static_cast<u32>(p_out / 4), nvec = kQT * vpr;
+        tp.vec_magic = (65536u + vpr - 1) / vpr;
+        for (u32 v = 0; v < nvec; ++v)
+            if (((v * tp.vec_magic) >> 16) != v / vpr) return false;   // cannot happen for vpr <= 26, checked anyway
+    }
     tp.slice_stride = static_cast<u32>(lane_stride);
     tp.group_stride = static_cast<u32>(group_stride);
     tp.smem_bytes = static_cast<u32>(smem);
