@@ -252,7 +252,7 @@ def run_b200(args, rank, local_rank, world):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"single synthetic {rate} Hz {args.seconds:g}-s APT recording per GPU "
                                    f"(BASELINE configs[1])", "profile": "standard", "samples_per_recording": int(n),
-                       "work_samples": int(n_work), "rows": int(produced // 2080),
+                       "work_samples": int(n_work), "rows": int(produced // 2080), "sync_roots": int(counts["n_roots"]),
                        "l2": "inputs_exceed_l2 (172.8 MB f32 input per step > 126 MB L2)",
                        "sharding": "one recording per GPU, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(4 * n),

@@ -182,6 +182,8 @@ int apt_decoder_wait(apt_decoder *dec, uint64_t *nout);
 /* Introspection after a wait(): sync positions found (decode.rs:110), N_w, rows. */
 int apt_decoder_last_sync(apt_decoder *dec, uint64_t *positions, size_t cap, size_t *npositions);
 int apt_decoder_last_counts(apt_decoder *dec, uint64_t *n_work, uint64_t *n_rows, uint64_t *n_peaks);
+/* Number of "roots" of the sync correlation the peak picker worked on in the last job (diagnostic). */
+int apt_decoder_last_root_count(apt_decoder *dec, uint64_t *n_roots);
 /* Copy an intermediate signal of the last job back to the host (what Context::step would dump):
  * which = 0 "demodulation_result" input i.e. resample+envelope output, 1 "filter_result",
  * 2 "sync_correlation". */
@@ -212,12 +214,12 @@ int apt_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
 
 /* Geometry of the tiled sm_100a resampler for a ratio L/M and a tap set (DESIGN.md "Tiled polyphase
  * kernel"); host code, no GPU.  usable == 0: the shape falls back to the generic kernel.  Optional
- * outputs: tile_taps (groups*group_stride floats; per group, per loop iteration, per slice lane a record of
- * slice_stride floats: taps of half A [4 samples][4 outputs], of half B likewise, padding) and
+ * outputs: tile_taps (groups*group_stride floats; per group one sub-table per slice lane, slice_stride floats
+ * apart, holding per loop iteration a 32-float record: taps of half A [4 samples][4 outputs], then half B) and
  * group_xs (groups entries: first input sample of each group relative to its row). */
 typedef struct apt_tile_info {
     uint32_t usable, groups, p_out, p_in, usteps, row_len, rows_per_tile, smem_bytes, slices, slice_stride,
-        half_taps, shift, iters, group_stride, ctas_per_sm;
+        half_taps, shift, iters, group_stride, ctas_per_sm, pair_pitch;
 } apt_tile_info;
 int apt_tile_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_tile_info *info,
                   float *tile_taps, size_t cap_taps, uint32_t *group_xs, size_t cap_groups);

@@ -47,7 +47,7 @@ class CFilter(C.Structure):
 class CTileInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("usable", "groups", "p_out", "p_in", "usteps", "row_len", "rows_per_tile",
                                           "smem_bytes", "slices", "slice_stride", "half_taps", "shift", "iters",
-                                          "group_stride", "ctas_per_sm")]
+                                          "group_stride", "ctas_per_sm", "pair_pitch")]
 
 
 STATUS_CB = C.CFUNCTYPE(None, C.c_float, C.c_char_p, C.c_void_p)
@@ -88,6 +88,7 @@ SIGNATURES = {
     "apt_decoder_wait": (C.c_int, [C.c_void_p, _u64p]),
     "apt_decoder_last_sync": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, _szp]),
     "apt_decoder_last_counts": (C.c_int, [C.c_void_p, _u64p, _u64p, _u64p]),
+    "apt_decoder_last_root_count": (C.c_int, [C.c_void_p, _u64p]),
     "apt_decoder_read_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, _u64p]),
     "apt_decoder_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "apt_decoder_kernel_count": (C.c_int, [C.c_void_p]),

@@ -82,6 +82,7 @@ int alloc_sync_buffers(apt_decoder *d) {
     d->pick = pick_scratch_carve(d->d_pick, d->max_blocks, d->max_positions, cap);
     APT_CUDA(cudaMemset(d->pick.ticket, 0, 8));
     if (getenv("APTB200_SEQUENTIAL_PICK")) d->use_parallel_pick = false;
+    if (getenv("APTB200_GENERIC_LOWPASS")) d->use_fused_lowpass = false;
     return APT_OK;
 }
 
@@ -553,6 +554,12 @@ extern "C" int apt_decoder_last_counts(apt_decoder *d, uint64_t *n_work, uint64_
     return APT_OK;
 }
 
+extern "C" int apt_decoder_last_root_count(apt_decoder *d, uint64_t *n_roots) {
+    if (!d || !n_roots) return fail(APT_ERR_BAD_ARG, "null argument");
+    *n_roots = d->h_res ? d->h_res->n_roots : 0;
+    return APT_OK;
+}
+
 extern "C" int apt_decoder_read_stage(apt_decoder *d, int which, float *out, uint64_t cap, uint64_t *n) {
     if (!d || !n) return fail(APT_ERR_BAD_ARG, "null argument");
     APT_CUDA(cudaSetDevice(d->device));
@@ -691,7 +698,8 @@ extern "C" int apt_tile_plan(uint32_t l, uint32_t m, const float *taps, size_t n
     memset(info, 0, sizeof(*info));
     if (!make_tile_plan(l, m, h, tp, tt, xs)) return APT_OK;
     *info = apt_tile_info{1, tp.groups, tp.p_out, tp.p_in, tp.usteps, tp.row_len, tp.qt, tp.smem_bytes, 4,
-                          tp.slice_stride, tp.half_taps, tp.shift, tp.iters, tp.group_stride, tp.ctas_per_sm};
+                          tp.slice_stride, tp.half_taps, tp.shift, tp.iters, tp.group_stride, tp.ctas_per_sm,
+                          tp.pair_pitch};
     if (tile_taps) memcpy(tile_taps, tt.data(), std::min(cap_taps, tt.size()) * sizeof(float));
     if (group_xs) memcpy(group_xs, xs.data(), std::min(cap_groups, xs.size()) * sizeof(u32));
     return APT_OK;

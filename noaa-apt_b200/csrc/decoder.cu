@@ -126,7 +126,7 @@ int run_find_sync(apt_decoder *d, uint64_t nwork) {
     const uint32_t glen = static_cast<uint32_t>(p.guard.size());
     const uint64_t ncorr = nwork - glen;
     const uint32_t nblocks = static_cast<uint32_t>((ncorr + p.dist - 1) / p.dist);
-    {
+    if (!d->job_corr_done) {
         Prof pr(d, "sync_correlation");
         APT_TRY(launch_corr(c, d->d_f, ncorr, d->d_guard, glen, d->d_corr));
     }
@@ -143,7 +143,7 @@ int run_find_sync(apt_decoder *d, uint64_t nwork) {
     return APT_OK;
 }
 
-static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n, uint64_t nwork) {
+static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n, uint64_t nwork, bool want_corr) {
     const Plan &p = d->plan;
     const LaunchCtx c{d->stream, d->sm_count};
     if (d->cb) {
@@ -171,9 +171,16 @@ static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n,
         APT_TRY(launch_envelope(c, d->d_r, nwork, p.cosphi2, p.sinphi, d->d_e));
     }
     if (d->cb) d->cb(0.42f, "Filtering", d->cb_user);                       // decode.rs:93
-    {
+    d->job_corr_done = false;
+    const u32 ntaps = static_cast<u32>(p.lp.size());
+    if (d->use_fused_lowpass && lowpass_corr_supported(ntaps, p.dec) && p.work_multiple) {
+        // low-pass and (when syncing) the sync cross-correlation in one pass over the envelope
+        Prof pr(d, want_corr ? "lowpass_correlation" : "lowpass");
+        APT_TRY(launch_lowpass_corr(c, d->d_e, nwork, p.lp.data(), ntaps, p.dec, d->d_f, want_corr ? d->d_corr : nullptr));
+        d->job_corr_done = want_corr;
+    } else {
         Prof pr(d, "lowpass");
-        APT_TRY(launch_fir_decimate(c, d->d_e, APT_F32, d->d_lp, static_cast<u32>(p.lp.size()), 1, nwork, d->d_f));
+        APT_TRY(launch_fir_decimate(c, d->d_e, APT_F32, d->d_lp, ntaps, 1, nwork, d->d_f));
     }
     return APT_OK;
 }
@@ -186,7 +193,7 @@ int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int 
     d->job_work = nwork;
     d->ev_used = 0;
 
-    APT_TRY(enqueue_front(d, in, format, n, nwork));
+    APT_TRY(enqueue_front(d, in, format, n, nwork, sync && p.work_multiple && d->d_corr != nullptr));
 
     if (sync) {
         if (d->cb) d->cb(0.5f, "Syncing", d->cb_user);                      // decode.rs:107

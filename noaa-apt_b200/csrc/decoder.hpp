@@ -73,6 +73,8 @@ struct apt_decoder {
     void *d_pick = nullptr;        // scratch of the parallel picker
     aptb200::PickScratch pick{};
     bool use_parallel_pick = true;
+    bool use_fused_lowpass = true;
+    bool job_corr_done = false;    // the correlation of the current job was produced by the fused low-pass kernel
     float *d_out = nullptr;        // rows for submit_host
     aptb200::SyncResult *h_res = nullptr;   // pinned
 

@@ -2,11 +2,14 @@
 #include "launch.hpp"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "aptb200.h"
 #include "common.hpp"
 #include "kernels_fast.cuh"
 #include "kernels_generic.cuh"
+#include "kernels_lpsync.cuh"
 #include "kernels_sync.cuh"
 
 namespace aptb200 {
@@ -57,20 +60,39 @@ int launch_polyphase_tiled(const LaunchCtx &c, const float *signal, u64 len, con
     if (nout == 0) return APT_OK;
     const u64 tile_out = static_cast<u64>(tp.qt) * tp.p_out;
     const u64 ntiles = (nout + tile_out - 1) / tile_out;
-    const unsigned grid = static_cast<unsigned>(std::min<u64>(ntiles, static_cast<u64>(c.sm_count) * tp.ctas_per_sm));
-    const unsigned block = 32 * tp.groups;
+    const unsigned grid = static_cast<unsigned>(std::min<u64>(ntiles, static_cast<u64>(c.sm_count)));
+    const unsigned block = 32 * (tp.groups + kWsEpilogueWarps + 1);   // compute + epilogue + producer warps
+    unsigned long long *prof = nullptr;
+    if (getenv("APTB200_TILE_PROFILE")) {
+        APT_CUDA(cudaMalloc(&prof, 512 * sizeof(unsigned long long)));
+        APT_CUDA(cudaMemsetAsync(prof, 0, 512 * sizeof(unsigned long long), c.stream));
+    }
     if (envelope) {
-        auto kern = k_polyphase_tiled_f32<true>;
+        auto kern = k_polyphase_ws<true>;
         APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem_bytes)));
         kern<<<grid, block, tp.smem_bytes, c.stream>>>(signal, len, tile_taps, group_xs, tp, nout, ntiles, cosphi2,
-                                                        sinphi, out);
+                                                        sinphi, out, prof);
     } else {
-        auto kern = k_polyphase_tiled_f32<false>;
+        auto kern = k_polyphase_ws<false>;
         APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem_bytes)));
         kern<<<grid, block, tp.smem_bytes, c.stream>>>(signal, len, tile_taps, group_xs, tp, nout, ntiles, cosphi2,
-                                                        sinphi, out);
+                                                        sinphi, out, prof);
     }
     APT_CUDA(cudaGetLastError());
+    if (prof) {
+        unsigned long long h[512];
+        APT_CUDA(cudaStreamSynchronize(c.stream));
+        APT_CUDA(cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(prof);
+        fprintf(stderr, "[tile profile, CTA 0, %llu tiles, cycles] producer: wait_empty %llu issue %llu | compute warp 0: wait_full %llu "
+                        "main %llu wait_planes %llu write_planes %llu | epilogue warp 0: wait_full %llu work %llu\n",
+                h[8], h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+        unsigned long long mn = ~0ull, mx = 0, sum = 0;
+        for (unsigned b = 0; b < grid; ++b) { mn = std::min(mn, h[16 + 2 * b]); mx = std::max(mx, h[16 + 2 * b]); sum += h[16 + 2 * b]; }
+        fprintf(stderr, "[tile profile] per-CTA kernel-body cycles: min %llu avg %llu max %llu; first 12:", mn, sum / grid, mx);
+        for (unsigned b = 0; b < 12 && b < grid; ++b) fprintf(stderr, " %llu(sm%llu)", h[16 + 2 * b], h[17 + 2 * b]);
+        fprintf(stderr, "\n");
+    }
     return APT_OK;
 }
 
@@ -96,6 +118,26 @@ int launch_envelope(const LaunchCtx &c, const float *x, u64 n, float cosphi2, fl
 int launch_corr(const LaunchCtx &c, const float *f, u64 ncorr, const int8_t *guard, u32 glen, float *corr) {
     if (ncorr == 0) return APT_OK;
     k_corr_generic<<<grid_for(ncorr, 256, c.sm_count), 256, 0, c.stream>>>(f, ncorr, guard, glen, corr);
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+bool lowpass_corr_supported(u32 ntaps, u32 pw) {
+    return (ntaps == 37 && pw == 3) || (ntaps == 43 && pw == 4) || (ntaps == 61 && pw == 5);
+}
+
+int launch_lowpass_corr(const LaunchCtx &c, const float *e, u64 n, const float *taps_host, u32 ntaps, u32 pw, float *f,
+                        float *corr) {
+    if (n == 0) return APT_OK;
+    LpTaps t{};
+    for (u32 j = 0; j < ntaps && j < 64; ++j) t.c[j] = taps_host[j];
+    const u64 ncorr = n > 38ull * pw ? n - 38ull * pw : 0;
+    const u64 ntiles = (n + kLpTile - 1) / kLpTile;
+    const unsigned grid = static_cast<unsigned>(std::min<u64>(ntiles, static_cast<u64>(c.sm_count) * 6));
+    if (ntaps == 37 && pw == 3) k_lowpass_corr<37, 3><<<grid, 256, 0, c.stream>>>(e, n, ncorr, t, f, corr);
+    else if (ntaps == 43 && pw == 4) k_lowpass_corr<43, 4><<<grid, 256, 0, c.stream>>>(e, n, ncorr, t, f, corr);
+    else if (ntaps == 61 && pw == 5) k_lowpass_corr<61, 5><<<grid, 256, 0, c.stream>>>(e, n, ncorr, t, f, corr);
+    else return fail(APT_ERR_BAD_ARG, "no fused low-pass/correlation kernel for %u taps, pixel width %u", ntaps, pw);
     APT_CUDA(cudaGetLastError());
     return APT_OK;
 }

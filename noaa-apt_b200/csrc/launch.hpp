@@ -43,12 +43,14 @@ struct TilePlan {
     u32 half_taps;     // padded taps of one half (4 outputs), multiple of 16
     u32 shift;         // half B's window starts this many samples after half A's (multiple of 16)
     u32 iters;         // loop iterations = usteps / 16
-    u32 row_len;       // floats per shared-memory row: multiple of 4, row_len/4 odd
-    u32 rows_floats;   // floats of the row buffer (also holds the partial-sum planes)
+    u32 row_len;       // samples of one row the kernel may touch (multiple of 4)
+    u32 pair_pitch;    // floats between consecutive row pairs in shared memory (rows 2i, 2i+1 share one bulk copy)
+    u32 rows_floats;   // floats of the rows of one stage (qt * row_len)
     u32 plane_pitch;   // floats per row of a partial-sum plane (p_out + 4)
     u32 vec_magic;     // (v * vec_magic) >> 16 == v / (p_out/4) for every v < qt*p_out/4
     u32 qt;            // rows (super-periods) per tile
-    u32 slice_stride;  // floats per (iteration, slice lane) tap record: 16 A + 16 B + 4 pad
+    u32 slice_stride;  // floats between the tap sub-tables of the 4 slice lanes (iters*32 + 8)
+    u32 stage_floats;  // floats of one row stage (rows + halo row)
     u32 group_stride;  // floats of one group's tap table
     u32 smem_bytes;    // dynamic shared memory
     u32 ctas_per_sm;   // 2 when two CTAs fit an SM, else 1
@@ -72,6 +74,11 @@ int launch_fir_decimate(const LaunchCtx &c, const void *signal, int format, cons
 int launch_envelope(const LaunchCtx &c, const float *x, u64 n, float cosphi2, float sinphi, float *out);
 // sync cross-correlation (decode.rs:225-233).
 int launch_corr(const LaunchCtx &c, const float *f, u64 ncorr, const int8_t *guard, u32 glen, float *corr);
+// Fused low-pass + sync correlation (kernels_lpsync.cuh).  Returns false when (ntaps, pixel width) has no
+// instantiation -- the caller then uses launch_fir_decimate + launch_corr.  corr == nullptr: low-pass only.
+bool lowpass_corr_supported(u32 ntaps, u32 pixel_width);
+int launch_lowpass_corr(const LaunchCtx &c, const float *e, u64 n, const float *taps_host, u32 ntaps, u32 pixel_width,
+                        float *f, float *corr);
 // roots of the correlation (see kernels_sync.cuh).
 int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32 *root_list, u32 *root_count,
                  SyncResult *result, const PickScratch *scratch /* nullptr: no dense numbering */);

@@ -11,7 +11,7 @@ namespace {
 constexpr u32 kR = 8, kH = 4, kQ = 4, kKS = 4, kQT = (32 / kKS) * kQ;
 constexpr u32 kMaxGroups = 13;                 // warps per CTA the kernel is compiled for (416 threads)
 constexpr u32 kSmemTwoCtas = (233472 - 2 * 1024) / 2 - 512;   // dynamic bytes that still let two CTAs share an SM
-constexpr u32 kSmemOneCta = 227 * 1024 - 512;
+constexpr u32 kSmemOneCta = 227 * 1024;
 constexpr u32 kIterSamples = 4 * kKS;          // samples consumed per loop iteration (one 16-byte chunk per slice lane)
 }  // namespace
 
@@ -67,18 +67,30 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
     if (!have) return false;
     const u64 span = ua + shift;                                              // samples a group reads per row
     const u64 iters = span / kIterSamples;
-    u64 row_len = (max_w0 + span + 3) / 4 * 4;
-    row_len = std::max(row_len, (p_in + 3) / 4 * 4);
-    if ((row_len / 4) % 2 == 0) row_len += 4;            // odd pitch in 16-byte units: conflict-free LDS.128
+    // Rows are staged in pairs: one bulk copy brings rows 2i and 2i+1 (they are p_in apart in the signal and
+    // overlap), pairs are pair_pitch floats apart.  pair_pitch is padded until the 8 row lanes of a quarter-warp
+    // (rows r = 0..7: pair r/2, half r%2) start in 8 different 16-byte bank groups -> conflict-free LDS.128.
+    const u64 row_len = (max_w0 + span + 3) / 4 * 4;     // samples of one row the kernel may touch
+    u64 pair_pitch = p_in + row_len;
+    for (;; pair_pitch += 4) {
+        u32 seen = 0;
+        for (u32 r = 0; r < 8; ++r) seen |= 1u << (((r >> 1) * (pair_pitch / 4) + (r & 1) * (p_in / 4)) % 8);
+        if (seen == 0xFF) break;
+        if (pair_pitch > p_in + row_len + 64) return false;
+    }
 
-    // Tap table [group][iteration][slice lane][36]: 16 floats for half A (4 u x 4 r), 16 for half B, 4 pad --
-    // the pad skews the four slice lanes of a warp onto different 16-byte bank groups.
-    const u64 lane_stride = 2 * 4 * kH + 4;
-    const u64 group_stride = iters * kKS * lane_stride;
+    // Tap table [group][slice lane][iteration][32]: 16 floats for half A (4 samples x 4 outputs), 16 for half B.
+    // Each slice lane's sub-table is followed by 8 floats of padding, which skews the four slice lanes of a
+    // warp onto different 16-byte bank groups (sub-table stride/4 = 2 mod 8).
+    const u64 rec = 2 * 4 * kH;                          // 32 floats per (iteration, slice lane)
+    const u64 lane_stride = iters * rec + 8;             // floats between the sub-tables of one group
+    const u64 group_stride = kKS * lane_stride;
     const u64 plane_pitch = p_out + 4;                   // partial-sum planes [slice][row][p_out + 4]
-    u64 rows_floats = static_cast<u64>(kQT) * row_len;
-    rows_floats = std::max(rows_floats, kKS * static_cast<u64>(kQT) * plane_pitch);   // planes alias the rows
-    const u64 smem = 16 + groups * group_stride * 4 + rows_floats * 4 + span * 4;
+    const u64 rows_floats = static_cast<u64>(kQT / 2) * pair_pitch;
+    // warp-specialised kernel: barriers + taps + 2 row stages (each with its halo row) + partial-sum planes
+    const u64 stage_floats = rows_floats + span;
+    const u64 planes_floats = kKS * static_cast<u64>(kQT) * plane_pitch;
+    const u64 smem = 128 + (groups * group_stride + 2 * stage_floats + planes_floats) * 4;
     if (smem > kSmemOneCta) return false;
     if ((plane_pitch / 4) % 2 == 0) return false;        // p_out/4 must be even (8 | p_out): always true
 
@@ -90,7 +102,7 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
         const u64 k0 = static_cast<u64>(kR) * g;
         for (u64 it = 0; it < iters; ++it) {
             for (u32 ks = 0; ks < kKS; ++ks) {
-                float *dst = &tile_taps[g * group_stride + (it * kKS + ks) * lane_stride];
+                float *dst = &tile_taps[g * group_stride + ks * lane_stride + it * rec];
                 for (u32 uu = 0; uu < 4; ++uu) {
                     const u64 u = (it * kKS + ks) * 4 + uu;             // sample index relative to w0
                     const long long x = static_cast<long long>(group_xs[g] + u);
@@ -114,6 +126,7 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
     tp.shift = static_cast<u32>(shift);
     tp.iters = static_cast<u32>(iters);
     tp.row_len = static_cast<u32>(row_len);
+    tp.pair_pitch = static_cast<u32>(pair_pitch);
     tp.rows_floats = static_cast<u32>(rows_floats);
     tp.plane_pitch = static_cast<u32>(plane_pitch);
     tp.qt = kQT;
@@ -126,7 +139,8 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
     tp.slice_stride = static_cast<u32>(lane_stride);
     tp.group_stride = static_cast<u32>(group_stride);
     tp.smem_bytes = static_cast<u32>(smem);
-    tp.ctas_per_sm = smem <= kSmemTwoCtas ? 2 : 1;
+    tp.ctas_per_sm = 1;
+    tp.stage_floats = static_cast<u32>(stage_floats);
     tp.off2 = off2;
     tp.debug = 0;
     if (const char *e = getenv("APTB200_TILE_DEBUG")) tp.debug = static_cast<u32>(atoi(e));

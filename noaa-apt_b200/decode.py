@@ -156,7 +156,9 @@ class Decoder:
     def last_counts(self):
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         raise_for(self._lib.apt_decoder_last_counts(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return {"n_work": a.value, "n_rows": b.value, "n_peaks": c.value}
+        r = C.c_uint64(0)
+        raise_for(self._lib.apt_decoder_last_root_count(self._h, C.byref(r)))
+        return {"n_work": a.value, "n_rows": b.value, "n_peaks": c.value, "n_roots": r.value}
 
     def read_stage(self, which):
         idx = {"demodulated": 0, "filtered": 1, "correlation": 2}[which] if isinstance(which, str) else int(which)

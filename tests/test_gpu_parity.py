@@ -120,8 +120,10 @@ def _oracle_filtered(rate, seconds, seed):
 
 @pytest.mark.parametrize("work_rate", [12480, 16640, 20800])
 def test_find_sync_positions_and_correlation(work_rate):
+    prof = na.Settings.profile({12480: "standard", 16640: "fast", 20800: "slow"}[work_rate])
     s = oracle.default_settings()
-    s.work_rate = work_rate
+    s.work_rate, s.resample_atten, s.resample_delta_freq = work_rate, prof.resample_atten, prof.resample_delta_freq
+    s.resample_cutout, s.demodulation_atten = prof.resample_cutout, prof.demodulation_atten
     x = synth.apt_signal(11025, 20, seed=3)
     _, st = oracle.decode_steps(x, 11025, s)
     f = st["filtered"]
@@ -129,6 +131,14 @@ def test_find_sync_positions_and_correlation(work_rate):
     ref_pos, ref_corr = oracle.find_sync(f, work_rate, want_corr=True)
     assert np.array_equal(corr.view(np.uint32), ref_corr.view(np.uint32))   # adds only, same order
     assert np.array_equal(pos, ref_pos)
+    # inside decode() the correlation comes from the fused low-pass kernel (box sums: different summation
+    # order, same values to fp32 rounding) -- the positions must still be the reference's
+    with na.Decoder(11025, na.Settings.profile({12480: "standard", 16640: "fast", 20800: "slow"}[work_rate]),
+                    max_samples=x.size) as dec:
+        dec.decode(x)
+        assert np.array_equal(dec.last_sync(), st["sync_pos"])
+        assert nerr(dec.read_stage("correlation"), ref_corr) <= TOL
+        assert nerr(dec.read_stage("filtered"), f) <= TOL
 
 
 def test_find_sync_on_noise_and_silence(rng):
