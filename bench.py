@@ -39,8 +39,10 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rate", type=int, default=48000, help="input sample rate (Hz)")
     ap.add_argument("--seconds", type=float, default=900.0, help="recording length")
-    ap.add_argument("--cpu-seconds", type=float, default=180.0,
+    ap.add_argument("--cpu-seconds", type=float, default=300.0,
                     help="length of the recording slice the CPU arms decode per step")
+    ap.add_argument("--batch", type=int, default=1,
+                    help="recordings decoded per GPU per step, one per CUDA stream (BASELINE configs[3]: 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -155,22 +157,32 @@ def run_b200(args, rank, local_rank, world):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    rate, K, W = args.rate, args.steps, max(args.warmup, 3)
-    pcm = make_recording(rate, args.seconds, seed=rank)
-    n = pcm.size
+    from noaa_apt_b200 import sharding
+    rate, K, W, B = args.rate, args.steps, max(args.warmup, 3), max(args.batch, 1)
+    dev = f"cuda:{local_rank}"
     settings = na.Settings()
-    dec = na.Decoder(rate, settings, max_samples=n, device=local_rank)
+    # B recordings per GPU, one decoder (= one CUDA stream + workspaces) each; up to 4 distinct seeds are
+    # generated and replicated into separate device buffers
+    n_seeds = min(B, 4)
+    pcms = [make_recording(rate, args.seconds, seed=rank * 4 + k) for k in range(n_seeds)]
+    n = pcms[0].size
+    decs = [na.Decoder(rate, settings, max_samples=n, device=local_rank) for _ in range(B)]
+    dec = decs[0]
     bound = dec.out_bound(n)
 
-    # ---- device-resident arm ("value"): the Signal (f32, wav.rs:37) already in HBM ----
-    x_host = torch.from_numpy(pcm.astype(np.float32)).pin_memory()
-    x_dev = x_host.to(f"cuda:{local_rank}")
-    out_dev = torch.empty(bound, dtype=torch.float32, device=f"cuda:{local_rank}")
+    # ---- device-resident arm ("value"): the Signals (f32, wav.rs:37) already in HBM ----
+    x_hosts = [torch.from_numpy(p.astype(np.float32)).pin_memory() for p in pcms]
+    x_devs = [x_hosts[k % n_seeds].to(dev) if k < n_seeds else x_hosts[k % n_seeds].to(dev).clone() for k in range(B)]
+    out_devs = [torch.empty(bound, dtype=torch.float32, device=dev) for _ in range(B)]
     stream = torch.cuda.ExternalStream(dec.stream, device=local_rank)
 
     def step_device():
-        dec.submit_device(x_dev.data_ptr(), na._lib.F32, n, True, out_dev.data_ptr(), bound)
-        return dec.wait()
+        for k in range(B):
+            decs[k].submit_device(x_devs[k].data_ptr(), na._lib.F32, n, True, out_devs[k].data_ptr(), bound)
+        got = 0
+        for k in range(B):
+            got = decs[k].wait()
+        return got
 
     def barrier():
         torch.cuda.synchronize()
@@ -179,49 +191,54 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; device time between two events recorded on decoder 0's
+        stream after/before full-device synchronisation, so it spans the work of every stream."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = dec.launch_count
+        l0 = sum(d.launch_count for d in decs)
         e0.record(stream)
         for _ in range(steps):
             fn()
+        torch.cuda.synchronize()
         e1.record(stream)
         e1.synchronize()
-        torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-        if dist_on:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), dec.launch_count - l0
+        return ms, sum(d.launch_count for d in decs) - l0
 
     for _ in range(W):
         produced = step_device()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_total, launches = timed(step_device, K)
+    ms_local, launches = timed(step_device, K)
     clocks = sampler.stop()
+    value, ms_total = sharding.aggregate_throughput(B * n * K, ms_local, dist if dist_on else None, dev)
     ms_step = ms_total / K
-    value = world * n / (ms_step * 1e-3) / 1e6
 
     # ---- end-to-end arm: host buffers through the reference-facing call (H2D + D2H inside) ----
-    out_host = torch.empty(bound, dtype=torch.float32).pin_memory()
+    out_hosts = [torch.empty(bound, dtype=torch.float32).pin_memory() for _ in range(B)]
 
     def step_host():
-        dec.submit_host_ptr(x_host.data_ptr(), na._lib.F32, n, True, out_host.data_ptr(), bound)
-        return dec.wait()
+        for k in range(B):
+            decs[k].submit_host_ptr(x_hosts[k % n_seeds].data_ptr(), na._lib.F32, n, True, out_hosts[k].data_ptr(), bound)
+        got = 0
+        for k in range(B):
+            got = decs[k].wait()
+        return got
 
     for _ in range(2):
         produced_host = step_host()
-    e2e_ms_total, _ = timed(step_host, K)
-    e2e_ms = e2e_ms_total / K
-    e2e_value = world * n / (e2e_ms * 1e-3) / 1e6
+    e2e_local, _ = timed(step_host, K)
+    e2e_value, e2e_total = sharding.aggregate_throughput(B * n * K, e2e_local, dist if dist_on else None, dev)
+    e2e_ms = e2e_total / K
 
     # ---- roofline of the dominant kernel: CUDA events on the decoder's stream, per launch ----
     dec.set_profiling(True)
     acc = {}
     prof_steps = min(K, 10)
     for _ in range(prof_steps):
-        step_device()
+        # one recording alone on the GPU: the per-kernel times are not disturbed by the other streams
+        dec.submit_device(x_devs[0].data_ptr(), na._lib.F32, n, True, out_devs[0].data_ptr(), bound)
+        dec.wait()
         for name, ms in dec.kernel_times_ms():
             acc.setdefault(name, []).append(ms)
     dec.set_profiling(False)
@@ -241,7 +258,7 @@ def run_b200(args, rank, local_rank, world):
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            sl = pcm[: int(min(args.cpu_seconds, args.seconds) * rate)]
+            sl = pcms[0][: int(min(args.cpu_seconds, args.seconds) * rate)]
             v, dt = cpu_arm(sl, rate, steps=3, warmup=1)
             cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"first {sl.size / rate:g} s of the same recording, 3 timed decodes; C restatement of the "
@@ -250,20 +267,24 @@ def run_b200(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"single synthetic {rate} Hz {args.seconds:g}-s APT recording per GPU "
-                                   f"(BASELINE configs[1])", "profile": "standard", "samples_per_recording": int(n),
+            "config": {"workload": (f"single synthetic {rate} Hz {args.seconds:g}-s APT recording per GPU "
+                                    f"(BASELINE configs[1])" if B == 1 else
+                                    f"batch of {B} synthetic {rate} Hz {args.seconds:g}-s APT recordings per GPU, one per "
+                                    f"CUDA stream (BASELINE configs[3])"),
+                       "profile": "standard", "recordings_per_gpu": B, "samples_per_recording": int(n),
                        "work_samples": int(n_work), "rows": int(produced // 2080), "sync_roots": int(counts["n_roots"]),
                        "l2": "inputs_exceed_l2 (172.8 MB f32 input per step > 126 MB L2)",
                        "sharding": "one recording per GPU, no collective"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(4 * n),
-                    "d2h_bytes_per_step": int(4 * produced_host + 32), "input": "pinned host f32 Signal"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(4 * n * B),
+                    "d2h_bytes_per_step": int((4 * produced_host + 32) * B), "input": "pinned host f32 Signal"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    dec.close()
+    for d in decs:
+        d.close()
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()

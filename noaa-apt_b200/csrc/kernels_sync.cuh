@@ -33,72 +33,107 @@ __device__ void scan_root_counts(const u32 *root_count, u32 nblocks, u32 *block_
 // Writes the block's roots, ascending, to root_list[b*D ...] and their count to root_count[b].
 // Dynamic shared memory: 2*D floats.
 // ---------------------------------------------------------------------------------------------
+// Inclusive prefix scan over the CTA (one value per thread) with a binary op; warp shuffles + one smem hop.
+template <int THREADS, typename T, typename Op>
+__device__ __forceinline__ T block_scan_incl(T v, T identity, Op op, T *s_warp /* THREADS/32 entries */) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = op(v, t);
+    }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        T w = lane < THREADS / 32 ? s_warp[lane] : identity;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const T t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w = op(w, t);
+        }
+        if (lane < THREADS / 32) s_warp[lane] = w;
+    }
+    __syncthreads();
+    if (warp > 0) v = op(v, s_warp[warp - 1]);
+    __syncthreads();
+    return v;
+}
+
 template <int THREADS, int CHUNK>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, CHUNK <= 10 ? 4 : 2)
 k_roots(const float *__restrict__ corr, u64 ncorr, u32 dist, u32 *__restrict__ root_list,
         u32 *__restrict__ root_count, SyncResult *__restrict__ result, u32 *__restrict__ block_off,
         u32 *__restrict__ ticket) {
     extern __shared__ float sm[];
-    float *a = sm;             // a[0..D): this block, a[D..2D): next block (later: its prefix maxima)
-    __shared__ float s_suffix[THREADS];   // max of chunks strictly to the right, within this block
-    __shared__ float s_prefix[THREADS];   // max of chunks strictly to the left, within the next block
-    __shared__ u32 s_count[THREADS];
+    float *a = sm;             // a[0..D): this block, a[D..2D): next block
+    __shared__ float s_wf[THREADS / 32];
+    __shared__ u32 s_wu[THREADS / 32];
     __shared__ u32 s_seed;
 
     const float NEG = -INFINITY;
     const u32 tid = threadIdx.x;
     const u64 base = static_cast<u64>(blockIdx.x) * dist;
 
-    for (u32 i = tid; i < 2 * dist; i += THREADS) {
-        const u64 g = base + i;
-        a[i] = g < ncorr ? __ldg(corr + g) : NEG;
-    }
     if (tid == 0) s_seed = kNoSeed;
+    // 16-byte loads where the block start allows it (corr is 16-byte aligned; base may not be)
+    if ((dist & 3) == 0 && base + 2ull * dist <= ncorr) {
+        const float4 *src = reinterpret_cast<const float4 *>(corr + base);
+        for (u32 i = tid; i < dist / 2; i += THREADS) reinterpret_cast<float4 *>(a)[i] = __ldg(src + i);
+    } else {
+        for (u32 i = tid; i < 2 * dist; i += THREADS) {
+            const u64 g = base + i;
+            a[i] = g < ncorr ? __ldg(corr + g) : NEG;
+        }
+    }
     __syncthreads();
 
     // seed of the peak list: (0, 0.0) is replaced by the first corr[i] > 0.0 with i <= D
     // (decode.rs:208-209 with the else-if at :250 while i - 0 <= D).
     if (blockIdx.x == 0) {
+        u32 first = kNoSeed;
         for (u32 i = tid; i <= dist && i < 2 * dist; i += THREADS)
-            if (a[i] > 0.f) atomicMin(&s_seed, i);
+            if (a[i] > 0.f) { first = i; break; }
+        if (first != kNoSeed) atomicMin(&s_seed, first);
     }
 
     const u32 lo = tid * CHUNK;
     const u32 hi = min(lo + CHUNK, dist);   // chunk [lo, hi) of the block (may be empty)
-
+    float va[CHUNK], vb[CHUNK];
     float cmax_a = NEG, cmax_b = NEG;
-    for (u32 i = lo; i < hi; ++i) {
-        cmax_a = fmaxf(cmax_a, a[i]);
-        cmax_b = fmaxf(cmax_b, a[dist + i]);
+#pragma unroll
+    for (int c = 0; c < CHUNK; ++c) {
+        const u32 i = lo + c;
+        va[c] = i < hi ? a[i] : NEG;
+        vb[c] = i < hi ? a[dist + i] : NEG;
+        cmax_a = fmaxf(cmax_a, va[c]);
+        cmax_b = fmaxf(cmax_b, vb[c]);
     }
-    s_suffix[tid] = cmax_a;
-    s_prefix[tid] = cmax_b;
+    auto fmx = [](float x, float y) { return fmaxf(x, y); };
+    // prefix maxima over the next block's chunks; suffix maxima over this block's chunks (scan in reversed order:
+    // thread THREADS-1-t carries chunk t)
+    const float pre_incl = block_scan_incl<THREADS>(cmax_b, NEG, fmx, s_wf);
+    // a[] is no longer needed (the chunks are in registers): reuse it to reverse the thread order
     __syncthreads();
+    float *s_rev = sm;                       // THREADS floats
+    s_rev[THREADS - 1 - tid] = cmax_a;
+    __syncthreads();
+    const float rev_in = s_rev[tid];
+    const float suf_incl_rev = block_scan_incl<THREADS>(rev_in, NEG, fmx, s_wf);
+    s_rev[THREADS - 1 - tid] = suf_incl_rev; // back to chunk order: s_rev[t] = max of chunks >= t
+    __syncthreads();
+    const float right = tid + 1 < THREADS ? s_rev[tid + 1] : NEG;                   // chunks > tid of this block
+    __syncthreads();
+    s_rev[tid] = pre_incl;
+    __syncthreads();
+    const float left_excl = tid > 0 ? s_rev[tid - 1] : NEG;                         // chunks < tid of the next block
 
-    // exclusive suffix / prefix maxima over chunks (log-step scans in shared memory)
-    for (u32 step = 1; step < THREADS; step <<= 1) {
-        const float sv = tid + step < THREADS ? s_suffix[tid + step] : NEG;
-        const float pv = tid >= step ? s_prefix[tid - step] : NEG;
-        __syncthreads();
-        s_suffix[tid] = fmaxf(s_suffix[tid], sv);
-        s_prefix[tid] = fmaxf(s_prefix[tid], pv);
-        __syncthreads();
-    }
-    const float right = tid + 1 < THREADS ? s_suffix[tid + 1] : NEG;   // chunks > tid of this block
-    const float left = tid > 0 ? s_prefix[tid - 1] : NEG;              // chunks < tid of the next block
-
-    // prefix maxima of the next block's chunk, kept in registers (a[dist + i] is read by this thread only)
+    // prefix maxima inside the next block's chunk, then walk this block's chunk right-to-left
     float pm[CHUNK];
     {
-        float run = left;
+        float run = left_excl;
 #pragma unroll
-        for (int c = 0; c < CHUNK; ++c) {
-            const u32 i = lo + c;
-            if (i < hi) run = fmaxf(run, a[dist + i]);
-            pm[c] = run;
-        }
+        for (int c = 0; c < CHUNK; ++c) { run = fmaxf(run, vb[c]); pm[c] = run; }
     }
-    // walk the chunk right-to-left with the running suffix maximum
     u32 flags = 0;
     {
         float run = right;
@@ -106,28 +141,20 @@ k_roots(const float *__restrict__ corr, u64 ncorr, u32 dist, u32 *__restrict__ r
         for (int c = CHUNK - 1; c >= 0; --c) {
             const u32 i = lo + c;
             if (i < hi) {
-                const float v = a[i];
                 const float wmax = fmaxf(run, pm[c]);       // max of corr over (p, p+D]
-                if (base + i < ncorr && !(wmax > v)) flags |= 1u << c;
-                run = fmaxf(run, v);
+                if (base + i < ncorr && !(wmax > va[c])) flags |= 1u << c;
+                run = fmaxf(run, va[c]);
             }
         }
     }
-    s_count[tid] = __popc(flags);
-    __syncthreads();
-    // exclusive scan of the per-thread counts
-    for (u32 step = 1; step < THREADS; step <<= 1) {
-        const u32 v = tid >= step ? s_count[tid - step] : 0;
-        __syncthreads();
-        s_count[tid] += v;
-        __syncthreads();
-    }
-    u32 w = tid > 0 ? s_count[tid - 1] : 0;
+    const u32 cnt = __popc(flags);
+    const u32 incl = block_scan_incl<THREADS>(cnt, 0u, [](u32 x, u32 y) { return x + y; }, s_wu);
+    u32 w = incl - cnt;
     u32 *list = root_list + base;
 #pragma unroll
     for (int c = 0; c < CHUNK; ++c)
         if (flags & (1u << c)) list[w++] = static_cast<u32>(base + lo + c);
-    if (tid == THREADS - 1) root_count[blockIdx.x] = s_count[THREADS - 1];
+    if (tid == THREADS - 1) root_count[blockIdx.x] = incl;
     if (blockIdx.x == 0 && tid == 0) result->seed_index = s_seed;
     // the last CTA to finish numbers the roots densely (exclusive scan of the per-block counts)
     if (ticket != nullptr && last_cta_arrives(ticket)) scan_root_counts(root_count, gridDim.x, block_off);
@@ -248,13 +275,13 @@ __device__ __forceinline__ bool last_cta_arrives(u32 *ticket) {
 // Exclusive scan of root_count[0..nblocks) into block_off[0..nblocks]; 1024 threads.
 __device__ void scan_root_counts(const u32 *root_count, u32 nblocks, u32 *block_off) {
     __shared__ u32 s_tmp[32];
-    constexpr u32 T = 1024;
+    const u32 T = blockDim.x;                 // 512 (k_roots)
     const u32 tid = threadIdx.x;
     const u32 per = (nblocks + T - 1) / T;
     const u32 b0 = min(tid * per, nblocks), b1 = min(b0 + per, nblocks);
     u32 local = 0;
     for (u32 b = b0; b < b1; ++b) local += __ldcg(root_count + b);
-    const u32 incl = block_scan_inclusive_1024(local, s_tmp);
+    const u32 incl = block_scan_incl<512>(local, 0u, [](u32 x, u32 y) { return x + y; }, s_tmp);
     u32 run = incl - local;
     for (u32 b = b0; b < b1; ++b) { block_off[b] = run; run += __ldcg(root_count + b); }
     if (tid == T - 1) block_off[nblocks] = incl;

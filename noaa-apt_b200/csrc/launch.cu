@@ -26,9 +26,9 @@ template <int CHUNK>
 int roots_with_chunk(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32 nblocks, u32 *root_list,
                      u32 *root_count, SyncResult *result, const PickScratch *sc) {
     const size_t smem = 2ull * dist * sizeof(float);
-    auto kern = k_roots<1024, CHUNK>;
+    auto kern = k_roots<512, CHUNK>;
     APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<nblocks, 1024, smem, c.stream>>>(corr, ncorr, dist, root_list, root_count, result,
+    kern<<<nblocks, 512, smem, c.stream>>>(corr, ncorr, dist, root_list, root_count, result,
                                             sc ? sc->block_off : nullptr, sc ? sc->ticket : nullptr);
     APT_CUDA(cudaGetLastError());
     return APT_OK;
@@ -145,11 +145,11 @@ int launch_lowpass_corr(const LaunchCtx &c, const float *e, u64 n, const float *
 int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32 *root_list, u32 *root_count,
                  SyncResult *result, const PickScratch *sc) {
     const u32 nblocks = static_cast<u32>((ncorr + dist - 1) / dist);
-    const u32 need = (dist + 1023) / 1024;
-    if (need <= 5) return roots_with_chunk<5>(c, corr, ncorr, dist, nblocks, root_list, root_count, result, sc);
-    if (need <= 7) return roots_with_chunk<7>(c, corr, ncorr, dist, nblocks, root_list, root_count, result, sc);
-    if (need <= 9) return roots_with_chunk<9>(c, corr, ncorr, dist, nblocks, root_list, root_count, result, sc);
-    if (need <= 16) return roots_with_chunk<16>(c, corr, ncorr, dist, nblocks, root_list, root_count, result, sc);
+    const u32 need = (dist + 511) / 512;
+    if (need <= 10) return roots_with_chunk<10>(c, corr, ncorr, dist, nblocks, root_list, root_count, result, sc);
+    if (need <= 13) return roots_with_chunk<13>(c, corr, ncorr, dist, nblocks, root_list, root_count, result, sc);
+    if (need <= 17) return roots_with_chunk<17>(c, corr, ncorr, dist, nblocks, root_list, root_count, result, sc);
+    if (need <= 32) return roots_with_chunk<32>(c, corr, ncorr, dist, nblocks, root_list, root_count, result, sc);
     return fail(APT_ERR_BAD_ARG, "work rate too high for the sync picker (min_distance %u)", dist);
 }
 

@@ -1,0 +1,64 @@
+//! Raw FFI declarations for libaptb200.so (hand-written equivalent of what `bindgen include/aptb200.h`
+//! emits).  SOURCE ONLY: there is no Rust toolchain in the image this repository is built and tested in,
+//! so this file has never been compiled; the ABI it binds is exercised by the C++ and Python hosts.
+#![allow(non_camel_case_types, dead_code)]
+
+use std::os::raw::{c_char, c_float, c_int, c_void};
+
+pub const APT_OK: c_int = 0;
+pub const APT_ERR_RESAMPLE_TO_ZERO: c_int = 1;
+pub const APT_ERR_TOO_SHORT: c_int = 2;
+pub const APT_ERR_FEW_SYNC_FRAMES: c_int = 3;
+pub const APT_ERR_WORK_RATE: c_int = 4;
+pub const APT_ERR_RATE_OVERFLOW: c_int = 5;
+pub const APT_ERR_CUDA: c_int = 6;
+pub const APT_ERR_BAD_ARG: c_int = 7;
+pub const APT_ERR_NOMEM: c_int = 8;
+pub const APT_ERR_CAPACITY: c_int = 9;
+pub const APT_ERR_EMPTY_RESULT: c_int = 10;
+
+pub const APT_FILTER_NONE: c_int = 0;
+pub const APT_FILTER_LOWPASS: c_int = 1;
+pub const APT_FILTER_LOWPASS_DC: c_int = 2;
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct apt_settings {
+    pub work_rate: u32,
+    pub resample_atten: c_float,
+    pub resample_delta_freq: c_float,
+    pub resample_cutout: c_float,
+    pub demodulation_atten: c_float,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct apt_filter {
+    pub kind: c_int,
+    pub cutout_pi: c_float,
+    pub atten: c_float,
+    pub delta_w_pi: c_float,
+}
+
+pub type apt_status_cb = Option<unsafe extern "C" fn(progress: c_float, description: *const c_char, user: *mut c_void)>;
+
+#[link(name = "aptb200")]
+extern "C" {
+    pub fn apt_strerror(status: c_int) -> *const c_char;
+    pub fn apt_last_error() -> *const c_char;
+    pub fn apt_filter_resample(f: *mut apt_filter, input_rate: u32, output_rate: u32);
+    pub fn apt_filter_design(f: *const apt_filter, out: *mut c_float, cap: usize, n: *mut usize) -> c_int;
+    pub fn apt_freq_hz(f_hz: c_float, rate_hz: u32) -> c_float;
+    pub fn apt_resample_len(n: u64, input_rate: u32, output_rate: u32, f: *const apt_filter, nout: *mut u64) -> c_int;
+    pub fn apt_resample_with_filter(signal: *const c_float, n: u64, input_rate: u32, output_rate: u32,
+                                    f: *const apt_filter, out: *mut c_float, cap: u64, nout: *mut u64) -> c_int;
+    pub fn apt_demodulate(signal: *const c_float, n: u64, carrier_pi: c_float, out: *mut c_float) -> c_int;
+    pub fn apt_filter_signal(signal: *const c_float, n: u64, f: *const apt_filter, out: *mut c_float) -> c_int;
+    pub fn apt_find_sync(signal: *const c_float, n: u64, work_rate: u32, positions: *mut u64, cap: usize,
+                         npositions: *mut usize, corr: *mut c_float) -> c_int;
+    pub fn apt_decode_len_bound(n: u64, input_rate: u32, s: *const apt_settings, bound: *mut u64) -> c_int;
+    pub fn apt_decode(signal: *const c_float, n: u64, input_rate: u32, s: *const apt_settings, sync: c_int,
+                      out: *mut c_float, cap: u64, nout: *mut u64, cb: apt_status_cb, user: *mut c_void) -> c_int;
+    pub fn apt_decode_pcm16(pcm: *const i16, n: u64, input_rate: u32, s: *const apt_settings, sync: c_int,
+                            out: *mut c_float, cap: u64, nout: *mut u64, cb: apt_status_cb, user: *mut c_void) -> c_int;
+}
