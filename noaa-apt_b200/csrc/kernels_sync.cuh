@@ -157,7 +157,10 @@ k_roots(const float *__restrict__ corr, u64 ncorr, u32 dist, u32 *__restrict__ r
     if (tid == THREADS - 1) root_count[blockIdx.x] = incl;
     if (blockIdx.x == 0 && tid == 0) result->seed_index = s_seed;
     // the last CTA to finish numbers the roots densely (exclusive scan of the per-block counts)
-    if (ticket != nullptr && last_cta_arrives(ticket)) scan_root_counts(root_count, gridDim.x, block_off);
+    if (ticket != nullptr && last_cta_arrives(ticket)) {
+        scan_root_counts(root_count, gridDim.x, block_off);
+        if (tid == 0) ticket[1] = 0;           // arrival counter of k_pick_links' grid barriers
+    }
 }
 
 // Smallest root >= s.  Binary search in the block of s, then the first root of the following
@@ -308,19 +311,38 @@ __device__ __forceinline__ void first_root_dense(u32 s, u32 dist, u32 nblocks, c
     pos = b < nblocks ? root_list[static_cast<u64>(b) * dist] : 0xFFFFFFFFu;
 }
 
+// Grid-wide barrier for a cooperatively launched (co-resident) grid: monotonic arrival counter in global memory
+// (zeroed by k_roots' last CTA before this kernel starts; never reset while CTAs may still be polling it).
+__device__ __forceinline__ void grid_barrier(u32 *counter, u32 &target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        u32 seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
+}
+
+// Cooperative grid (all CTAs co-resident): J0 = F for every candidate, then pointer doubling with one grid
+// barrier per level -- every level is a single pass of <= 1 element per thread, so the cost is the ~12 barriers.
 __global__ void __launch_bounds__(1024)
 k_pick_links(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ root_list,
              const u32 *__restrict__ root_count, u32 nblocks, u32 *__restrict__ positions, u32 max_positions,
-             SyncResult *__restrict__ result, PickScratch sc, u32 smem_words) {
-    extern __shared__ u32 s_tab[];
+             SyncResult *__restrict__ result, PickScratch sc) {
     __shared__ u32 s_tmp[32];
     __shared__ u32 s_misc[4];
     const u32 tid = threadIdx.x;
     constexpr u32 T = 1024;
-    const u32 nroots = sc.block_off[nblocks];
+    const u32 gtid = blockIdx.x * T + tid, gsize = gridDim.x * T;
+    const u32 nroots = __ldcg(sc.block_off + nblocks);
     const u32 nr = static_cast<u32>((ncorr + row - 1) / row);      // A-type starts row*m < ncorr
     const u32 ncand = nr + nroots;
     const u32 END = ncand;
+    u32 bar_target = 0;
     if (ncand + 1 > sc.cap || nr + 1 > max_positions) {
         // too many roots for the scratch (e.g. silence: every index is a root): correct-but-slow path
         if (blockIdx.x == 0 && tid == 0) {
@@ -330,9 +352,8 @@ k_pick_links(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ ro
         return;
     }
 
-    // ---- J0 = F for this thread's candidate ----
-    const u32 c = blockIdx.x * T + tid;
-    if (c <= ncand) {
+    // ---- J0 = F for every candidate (and END) ----
+    for (u32 c = gtid; c <= ncand; c += gsize) {
         u32 nxt = END, s = 0xFFFFFFFFu, peak = 0;
         if (c < ncand) {
             u64 s64;
@@ -361,11 +382,8 @@ k_pick_links(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ ro
         sc.cand_peak[c] = peak;
         sc.ja[c] = nxt;
     }
-    if (!last_cta_arrives(sc.ticket)) return;
-
-    // ================= last CTA: orbit by pointer doubling =================
     // ---- the first start, from the seed (decode.rs:208-209) ----
-    if (tid == 0) {
+    if (gtid == 0) {
         const u32 seed = result->seed_index;
         u32 p1 = 0, start = END;
         u64 s2 = 2ull * row;
@@ -379,55 +397,44 @@ k_pick_links(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ ro
         positions[0] = p1;
         sc.orbit[0] = start;
     }
-    // jump tables: shared memory when both fit, else the global ping-pong buffers
-    const bool in_smem = 2ull * (ncand + 1) <= smem_words;
-    u32 *jc = in_smem ? s_tab : sc.ja;
-    u32 *jn = in_smem ? s_tab + (ncand + 1) : sc.jb;
-    if (in_smem)
-        for (u32 i = tid; i <= ncand; i += T) jc[i] = __ldcg(sc.ja + i);
-    __syncthreads();
+    grid_barrier(sc.ticket + 1, bar_target);
 
+    // ---- doubling: orbit[n + 2^k] = J_k[orbit[n]];  J_{k+1} = J_k o J_k ----
+    u32 *jc = sc.ja, *jn = sc.jb;
     const u32 max_events = min(nr + 1, max_positions);   // every event lands in a new row
     for (u32 span = 1; span < max_events; span <<= 1) {
-        for (u32 n = tid; n < span && n + span < max_events; n += T) sc.orbit[n + span] = jc[sc.orbit[n]];
-        if ((span << 1) < max_events) {
-            for (u32 c0 = tid; c0 <= ncand; c0 += 8 * T) {
-                u32 a[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { const u32 ci = c0 + i * T; a[i] = ci <= ncand ? jc[ci] : END; }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = jc[a[i]];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { const u32 ci = c0 + i * T; if (ci <= ncand) jn[ci] = a[i]; }
-            }
-        }
-        __syncthreads();
+        for (u32 n = gtid; n < span && n + span < max_events; n += gsize) sc.orbit[n + span] = __ldcg(jc + __ldcg(sc.orbit + n));
+        if ((span << 1) < max_events)
+            for (u32 c = gtid; c <= ncand; c += gsize) jn[c] = __ldcg(jc + __ldcg(jc + c));
+        grid_barrier(sc.ticket + 1, bar_target);
         u32 *t = jc; jc = jn; jn = t;
     }
 
     // ---- events -> positions (decode.rs:241-253); END is absorbing so events are a prefix of orbit[] ----
-    u32 my_events = 0;
-    for (u32 n = tid; n < max_events; n += T) {
-        const u32 v = sc.orbit[n];
+    for (u32 n = gtid; n < max_events; n += gsize) {
+        const u32 v = __ldcg(sc.orbit + n);
         if (v == END) continue;
-        ++my_events;
-        const u32 s = sc.cand_s[v];
+        const u32 s = __ldcg(sc.cand_s + v);
         const u32 target = s / row;
-        const u32 prev = n == 0 ? 1u : sc.cand_s[sc.orbit[n - 1]] / row;
+        const u32 prev = n == 0 ? 1u : __ldcg(sc.cand_s + __ldcg(sc.orbit + n - 1)) / row;
         for (u32 j = prev; j + 1 < target; ++j) positions[j] = s;      // duplicates pushed by the `while`
-        positions[target - 1] = sc.cand_peak[v];
+        positions[target - 1] = __ldcg(sc.cand_peak + v);
     }
+    grid_barrier(sc.ticket + 1, bar_target);
+    if (blockIdx.x != 0) return;
+
+    // ---- CTA 0: counts ----
+    u32 my_events = 0;
+    for (u32 n = tid; n < max_events; n += T) my_events += __ldcg(sc.orbit + n) != END;
     const u32 events = block_scan_inclusive_1024(my_events, s_tmp);
     if (tid == T - 1) s_misc[2] = events;
     __syncthreads();
     const u32 nev = s_misc[2];
-    const u32 npeaks = nev == 0 ? 1u : sc.cand_s[sc.orbit[nev - 1]] / row;
-    __syncthreads();
-
-    // ---- rows that fit (decode.rs:125-127): positions are non-decreasing -> count of the passing prefix ----
+    const u32 npeaks = nev == 0 ? 1u : __ldcg(sc.cand_s + __ldcg(sc.orbit + nev - 1)) / row;
+    // rows that fit (decode.rs:125-127): positions are non-decreasing -> count of the passing prefix
     u32 cnt = 0;
     for (u32 i = tid; i + 1 < npeaks; i += T)
-        if (static_cast<u64>(positions[i]) + row < nwork) ++cnt;
+        if (static_cast<u64>(__ldcg(positions + i)) + row < nwork) ++cnt;
     const u32 total_rows = block_scan_inclusive_1024(cnt, s_tmp);
     if (tid == T - 1) {
         result->n_peaks = npeaks;

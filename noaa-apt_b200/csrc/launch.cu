@@ -157,13 +157,16 @@ int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, con
                 const u32 *root_count, u32 nblocks, u32 *positions, u32 max_positions, SyncResult *result,
                 const PickScratch *scratch) {
     if (scratch) {
-        // one thread per candidate; the last CTA to finish walks the orbit with its jump tables in shared memory
-        constexpr size_t kSmem = 200 * 1024;
-        // (per device, cheap: not cached so that every GPU of a batch gets it)
-        APT_CUDA(cudaFuncSetAttribute(k_pick_links, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
-        const unsigned grid = (scratch->cap + 1 + 1023) / 1024;
-        k_pick_links<<<grid, 1024, kSmem, c.stream>>>(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions,
-                                                      max_positions, result, *scratch, static_cast<u32>(kSmem / 4));
+        // cooperative launch: the kernel's grid barriers need every CTA resident (1024 threads, no dynamic smem)
+        int per_sm = 0;
+        APT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pick_links, 1024, 0));
+        const unsigned want = (scratch->cap + 1 + 1023) / 1024;
+        const unsigned grid = std::max(1u, std::min(want, static_cast<unsigned>(std::max(per_sm, 1) * c.sm_count)));
+        PickScratch sc = *scratch;
+        void *args[] = {&ncorr, &nwork, &row, &dist, &root_list, &root_count, &nblocks, &positions, &max_positions,
+                        &result, &sc};
+        APT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_pick_links), dim3(grid), dim3(1024), args, 0,
+                                             c.stream));
     } else {
         k_pick_sequential<<<1, 32, 0, c.stream>>>(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions,
                                                   max_positions, result);
