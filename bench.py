@@ -231,6 +231,20 @@ def run_b200(args, rank, local_rank, world):
     e2e_value, e2e_total = sharding.aggregate_throughput(B * n * K, e2e_local, dist if dist_on else None, dev)
     e2e_ms = e2e_total / K
 
+    # same, handing over the WAV's PCM16 samples (apt_decode_pcm16's path: the `as f32` of wav.rs:37 runs on the GPU)
+    p_hosts = [torch.from_numpy(p.copy()).pin_memory() for p in pcms]
+
+    def step_host_pcm16():
+        for k in range(B):
+            decs[k].submit_host_ptr(p_hosts[k % n_seeds].data_ptr(), na._lib.PCM16, n, True, out_hosts[k].data_ptr(), bound)
+        for k in range(B):
+            decs[k].wait()
+
+    for _ in range(2):
+        step_host_pcm16()
+    p16_local, _ = timed(step_host_pcm16, K)
+    p16_value, p16_total = sharding.aggregate_throughput(B * n * K, p16_local, dist if dist_on else None, dev)
+
     # ---- roofline of the dominant kernel: CUDA events on the decoder's stream, per launch ----
     dec.set_profiling(True)
     acc = {}
@@ -249,8 +263,16 @@ def run_b200(args, rank, local_rank, world):
     dom = "resample_envelope"
     alg_bytes = 4 * n + 4 * n_work                      # read every input once, write every e once
     achieved = alg_bytes / (kernel_ms[dom] * 1e-3) / 1e9 if dom in kernel_ms else None
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_all_kernels_metrics.json")) as f:
+            for m in json.load(f):
+                if "k_polyphase_ws" in m["kernel"] and abs(args.seconds - 900.0) < 1e-6 and rate == 48000:
+                    traffic = (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) * 1e6
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_kind,
+                "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_kind,
                 "algorithmic_bytes": alg_bytes, "kernel_ms": kernel_ms.get(dom),
                 "all_kernels_ms": kernel_ms}
 
@@ -277,6 +299,8 @@ def run_b200(args, rank, local_rank, world):
                        "sharding": "one recording per GPU, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(4 * n * B),
                     "d2h_bytes_per_step": int((4 * produced_host + 32) * B), "input": "pinned host f32 Signal"},
+            "e2e_pcm16": {"value": p16_value, "unit": UNIT, "ms_per_step": p16_total / K, "h2d_bytes_per_step": int(2 * n * B),
+                          "input": "pinned host int16 (the WAV's samples); cast on the device"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -15,7 +15,8 @@
 using namespace aptb200;
 
 namespace aptb200 {
-int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int sync, float *rows_out);
+int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int sync, float *rows_out,
+                    const void *host_chunked);
 int run_find_sync(apt_decoder *d, uint64_t nwork);
 }  // namespace aptb200
 
@@ -53,11 +54,16 @@ int free_decoder_buffers(apt_decoder *d) {
     if (d->stream) cudaStreamSynchronize(d->stream);
     for (void *p : {(void *)d->d_h, (void *)d->d_lp, (void *)d->d_one, (void *)d->d_guard, d->d_in, (void *)d->d_r,
                     (void *)d->d_e, (void *)d->d_f, (void *)d->d_corr, (void *)d->d_aligned, (void *)d->d_root_list,
-                    (void *)d->d_root_count, (void *)d->d_pos, (void *)d->d_res, (void *)d->d_out, d->d_pick, (void *)d->d_tile_taps, (void *)d->d_tile_xs})
+                    (void *)d->d_root_count, (void *)d->d_pos, (void *)d->d_res, (void *)d->d_out, d->d_pick, (void *)d->d_tile_taps, (void *)d->d_tile_xs, (void *)d->d_conv})
         if (p) cudaFree(p);
     if (d->h_res) cudaFreeHost(d->h_res);
     for (auto e : d->ev_begin) cudaEventDestroy(e);
     for (auto e : d->ev_end) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (d->ev_copied[i]) cudaEventDestroy(d->ev_copied[i]);
+        if (d->ev_free[i]) cudaEventDestroy(d->ev_free[i]);
+    }
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
     if (d->stream) cudaStreamDestroy(d->stream);
     return APT_OK;
 }
@@ -239,11 +245,11 @@ extern "C" int apt_resample_with_filter(const float *signal, uint64_t n, uint32_
             APT_TRY(dg.alloc(xs.size() * sizeof(u32)));
             APT_CUDA(cudaMemcpy(dt.p, tt.data(), tt.size() * sizeof(float), cudaMemcpyHostToDevice));
             APT_CUDA(cudaMemcpy(dg.p, xs.data(), xs.size() * sizeof(u32), cudaMemcpyHostToDevice));
-            APT_TRY(launch_polyphase_tiled(c, dx.as<float>(), n, dh.as<float>(), dt.as<float>(), dg.as<u32>(), tp, rp.nout,
-                                           false, 0.f, 1.f, dy.as<float>()));
+            APT_TRY(launch_polyphase_tiled(c, dx.as<float>(), n, dt.as<float>(), dg.as<u32>(), tp, rp.nout, 0, 0, false, 0.f,
+                                           1.f, dy.as<float>()));
             APT_CUDA(cudaDeviceSynchronize());
         } else {
-            APT_TRY(launch_polyphase(c, dx.p, APT_F32, n, dh.as<float>(), rp.r.l, rp.r.m, off2, rp.nout, false, 0.f, 1.f,
+            APT_TRY(launch_polyphase(c, dx.p, APT_F32, n, dh.as<float>(), rp.r.l, rp.r.m, off2, 0, rp.nout, false, 0.f, 1.f,
                                      dy.as<float>()));
         }
     } else {
@@ -393,6 +399,13 @@ extern "C" int apt_decoder_create(int device, uint32_t input_rate, const apt_set
 
     APT_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     d->max_samples = max_samples;
+    {
+        // staging for host submits: whole recording up to 64 Mi samples, else two chunks of 32 Mi (APTB200_CHUNK_SAMPLES overrides)
+        uint64_t chunk = 32ull << 20;
+        if (const char *e = getenv("APTB200_CHUNK_SAMPLES")) chunk = std::max<uint64_t>(strtoull(e, nullptr, 10), 1u << 16);
+        d->chunk_samples = (max_samples > 2 * chunk && p.first_polyphase) ? chunk : 0;
+        if (getenv("APTB200_CHUNK_SAMPLES") && max_samples > chunk && p.first_polyphase) d->chunk_samples = chunk;
+    }
     d->max_work = plan_work_len(p, max_samples);
     d->max_out = plan_out_bound(p, max_samples);
     if (d->max_work >= (1ull << 32))
@@ -465,15 +478,41 @@ int submit_common(apt_decoder *d, const void *signal, int format, uint64_t n, in
 
     const void *dev_in = signal;
     float *rows_dst = out;
+    const void *host_chunked = nullptr;
     if (host) {
-        if (!d->d_in) APT_CUDA(cudaMalloc(&d->d_in, std::max<uint64_t>(d->max_samples, 1) * sizeof(float)));
+        // Recordings longer than the chunk size are uploaded in chunks that overlap the resampling; shorter ones
+        // (and the L == 1 first stage) are staged whole.
+        const bool chunked = d->chunk_samples != 0 && n > d->chunk_samples && p.first_polyphase;
+        if (d->chunk_samples != 0 && n > d->chunk_samples && !chunked)
+            return fail(APT_ERR_BAD_ARG, "recording longer than the staging buffer and the first stage is not polyphase");
+        const uint64_t stage_samples = d->chunk_samples ? 2 * d->chunk_samples : d->max_samples;
+        if (!d->d_in) APT_CUDA(cudaMalloc(&d->d_in, std::max<uint64_t>(stage_samples, 1) * sizeof(float)));
         if (!d->d_out) APT_CUDA(cudaMalloc(&d->d_out, std::max<uint64_t>(d->max_out, 1) * sizeof(float)));
-        APT_CUDA(cudaMemcpyAsync(d->d_in, signal, n * sample_bytes(format), cudaMemcpyHostToDevice, d->stream));
-        dev_in = d->d_in;
+        if (chunked) {
+            if (!d->copy_stream) {
+                APT_CUDA(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+                for (int i = 0; i < 2; ++i) {
+                    APT_CUDA(cudaEventCreateWithFlags(&d->ev_copied[i], cudaEventDisableTiming));
+                    APT_CUDA(cudaEventCreateWithFlags(&d->ev_free[i], cudaEventDisableTiming));
+                }
+            }
+            if (format == APT_PCM16 && d->conv_cap < d->chunk_samples) {
+                if (d->d_conv) APT_CUDA(cudaFree(d->d_conv));
+                d->d_conv = nullptr;
+                d->conv_cap = 0;
+                APT_CUDA(cudaMalloc(&d->d_conv, d->chunk_samples * sizeof(float)));
+                d->conv_cap = d->chunk_samples;
+            }
+            host_chunked = signal;
+            dev_in = nullptr;
+        } else {
+            APT_CUDA(cudaMemcpyAsync(d->d_in, signal, n * sample_bytes(format), cudaMemcpyHostToDevice, d->stream));
+            dev_in = d->d_in;
+        }
         rows_dst = d->d_out;
     }
     d->job_rows_src = rows_dst;
-    int st = decoder_enqueue(d, dev_in, format, n, sync, rows_dst);
+    int st = decoder_enqueue(d, dev_in, format, n, sync, rows_dst, host_chunked);
     if (st != APT_OK) {
         cudaStreamSynchronize(d->stream);
         d->job_status = st;

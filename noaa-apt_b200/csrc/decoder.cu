@@ -143,7 +143,87 @@ int run_find_sync(apt_decoder *d, uint64_t nwork) {
     return APT_OK;
 }
 
-static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n, uint64_t nwork, bool want_corr) {
+// fast_resampling + demodulate of outputs produced from a device-resident (or staged) chunk.
+// `in` is the address sample 0 of the recording would have (a biased pointer for chunk buffers).
+static int launch_front_polyphase(apt_decoder *d, const void *in, int format, uint64_t n, uint64_t nwork,
+                                  uint64_t tile_begin, uint64_t tile_end, uint64_t k_begin, uint64_t k_end,
+                                  float *conv_base /* f32 view of a PCM16 chunk (already biased) or nullptr */) {
+    const Plan &p = d->plan;
+    const LaunchCtx c{d->stream, d->sm_count};
+    if (p.tiled && d->d_tile_taps && (format == APT_F32 || conv_base)) {
+        const float *fin = format == APT_F32 ? static_cast<const float *>(in) : conv_base;
+        return launch_polyphase_tiled(c, fin, n, d->d_tile_taps, d->d_tile_xs, p.tile, nwork, tile_begin, tile_end, true,
+                                      p.cosphi2, p.sinphi, d->d_e);
+    }
+    return launch_polyphase(c, in, format, n, d->d_h, p.first.l, p.first.m, p.off2, k_begin, k_end ? k_end : nwork, true,
+                            p.cosphi2, p.sinphi, d->d_e);
+}
+
+// Long host recording: upload in chunks (with the filter-length overlap each chunk needs) on the copy stream while
+// the previous chunk is resampled on the compute stream.  Only the polyphase first stage is chunked.
+static int enqueue_front_chunked(apt_decoder *d, const void *host, int format, uint64_t n, uint64_t nwork) {
+    const Plan &p = d->plan;
+    const LaunchCtx c{d->stream, d->sm_count};
+    const size_t sb = format == APT_PCM16 ? 2 : 4;
+    const uint64_t cap = d->chunk_samples;
+    const bool tiled = p.tiled && d->d_tile_taps;
+    const uint64_t l = p.first.l, m = p.first.m;
+    uint64_t units, per_chunk;            // tiles or outputs
+    const uint64_t tile_in = static_cast<uint64_t>(p.tile.qt) * p.tile.p_in, tile_out = static_cast<uint64_t>(p.tile.qt) * p.tile.p_out;
+    if (tiled) {
+        units = (nwork + tile_out - 1) / tile_out;
+        if (cap < tile_in + p.tile.row_len + p.tile.p_in + 64) return fail(APT_ERR_BAD_ARG, "chunk too small for one tile");
+        per_chunk = (cap - p.tile.row_len - p.tile.p_in - 64) / tile_in;
+    } else {
+        units = nwork;
+        const uint64_t halo = p.off2 / l + 4;
+        if (cap < 2 * halo + 1024) return fail(APT_ERR_BAD_ARG, "chunk too small for the filter");
+        per_chunk = (cap - 2 * halo) * l / m;
+    }
+    if (per_chunk == 0) return fail(APT_ERR_BAD_ARG, "chunk too small");
+    char *stage[2] = {static_cast<char *>(d->d_in), static_cast<char *>(d->d_in) + cap * 4};
+    uint64_t chunk = 0;
+    for (uint64_t u0 = 0; u0 < units; u0 += per_chunk, ++chunk) {
+        const uint64_t u1 = std::min(units, u0 + per_chunk);
+        const int b = static_cast<int>(chunk & 1);
+        uint64_t xa, xb;
+        if (tiled) {
+            // first sample: the halo row of the chunk's first tile (window of the last group one super-period back)
+            xa = u0 == 0 ? 0 : u0 * tile_in - p.tile.p_in + d->plan.tile_xs.back();
+            xb = std::min<uint64_t>(n, (u1 * p.tile.qt - 1) * p.tile.p_in + p.tile.row_len);
+        } else {
+            const uint64_t kfirst = u0 == 0 ? 0 : u0 - 1;                    // the envelope needs r[k0 - 1]
+            xa = (kfirst * m + l - 1) / l;
+            xa &= ~static_cast<uint64_t>(7);                                  // keep 16-byte alignment of PCM16 chunks
+            xb = std::min<uint64_t>(n, ((u1 - 1) * m + p.off2) / l + 1);
+        }
+        if (xb <= xa || xb - xa > cap) return fail(APT_ERR_BAD_ARG, "internal: chunk geometry (%llu..%llu, cap %llu)",
+                                                   (unsigned long long)xa, (unsigned long long)xb, (unsigned long long)cap);
+        // copy stream: wait until the compute stream has finished with this buffer, then upload
+        if (chunk >= 2) APT_CUDA(cudaStreamWaitEvent(d->copy_stream, d->ev_free[b], 0));
+        APT_CUDA(cudaMemcpyAsync(stage[b], static_cast<const char *>(host) + xa * sb, (xb - xa) * sb, cudaMemcpyHostToDevice,
+                                 d->copy_stream));
+        APT_CUDA(cudaEventRecord(d->ev_copied[b], d->copy_stream));
+        APT_CUDA(cudaStreamWaitEvent(d->stream, d->ev_copied[b], 0));
+        // compute stream: (cast,) resample + envelope of this chunk's outputs
+        const void *in_biased = stage[b] - xa * sb;
+        float *conv_biased = nullptr;
+        if (format == APT_PCM16 && tiled) {
+            APT_TRY(launch_pcm16_to_f32(c, reinterpret_cast<const int16_t *>(stage[b]), xb - xa, d->d_conv));
+            d->launches++;
+            conv_biased = d->d_conv - xa;
+        }
+        d->launches++;
+        APT_TRY(launch_front_polyphase(d, in_biased, format, n, nwork, tiled ? u0 : 0, tiled ? u1 : 0, tiled ? 0 : u0,
+                                       tiled ? 0 : u1, conv_biased));
+        APT_CUDA(cudaEventRecord(d->ev_free[b], d->stream));
+    }
+    d->job_chunks = chunk;
+    return APT_OK;
+}
+
+static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n, uint64_t nwork, bool want_corr,
+                         const void *host_chunked) {
     const Plan &p = d->plan;
     const LaunchCtx c{d->stream, d->sm_count};
     if (d->cb) {
@@ -151,15 +231,29 @@ static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n,
         snprintf(msg, sizeof(msg), "Resampling to %u", p.st.work_rate);
         d->cb(0.1f, msg, d->cb_user);                                       // decode.rs:63
     }
+    d->job_chunks = 0;
     if (p.first_polyphase) {
         // fast_resampling + demodulate fused: r is never written (decode.rs:77,89)
         Prof pr(d, "resample_envelope");
-        if (p.tiled && format == APT_F32 && d->d_tile_taps)
-            APT_TRY(launch_polyphase_tiled(c, static_cast<const float *>(in), n, d->d_h, d->d_tile_taps, d->d_tile_xs,
-                                           p.tile, nwork, true, p.cosphi2, p.sinphi, d->d_e));
-        else
-            APT_TRY(launch_polyphase(c, in, format, n, d->d_h, p.first.l, p.first.m, p.off2, nwork, true, p.cosphi2,
-                                     p.sinphi, d->d_e));
+        if (host_chunked) {
+            APT_TRY(enqueue_front_chunked(d, host_chunked, format, n, nwork));
+        } else {
+            float *conv = nullptr;
+            if (format == APT_PCM16 && p.tiled && d->d_tile_taps && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+                // the WAV's int16 samples: `as f32` (wav.rs:37) on the device, then the same tiled kernel
+                if (d->conv_cap < n) {
+                    if (d->d_conv) APT_CUDA(cudaFree(d->d_conv));
+                    d->d_conv = nullptr;
+                    d->conv_cap = 0;
+                    APT_CUDA(cudaMalloc(&d->d_conv, std::max<uint64_t>(d->max_samples, n) * sizeof(float)));
+                    d->conv_cap = std::max<uint64_t>(d->max_samples, n);
+                }
+                APT_TRY(launch_pcm16_to_f32(c, static_cast<const int16_t *>(in), n, d->d_conv));
+                d->launches++;
+                conv = d->d_conv;
+            }
+            APT_TRY(launch_front_polyphase(d, in, format, n, nwork, 0, 0, 0, 0, conv));
+        }
         if (d->cb) d->cb(0.4f, "Demodulating", d->cb_user);                 // decode.rs:87
     } else {
         {
@@ -186,14 +280,15 @@ static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n,
 }
 
 // Enqueues the whole of decode() on the decoder's stream.  `in` and `rows_out` are device pointers.
-int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int sync, float *rows_out) {
+int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int sync, float *rows_out,
+                    const void *host_chunked) {
     const Plan &p = d->plan;
     const LaunchCtx c{d->stream, d->sm_count};
     const uint64_t nwork = plan_work_len(p, n);
     d->job_work = nwork;
     d->ev_used = 0;
 
-    APT_TRY(enqueue_front(d, in, format, n, nwork, sync && p.work_multiple && d->d_corr != nullptr));
+    APT_TRY(enqueue_front(d, in, format, n, nwork, sync && p.work_multiple && d->d_corr != nullptr, host_chunked));
 
     if (sync) {
         if (d->cb) d->cb(0.5f, "Syncing", d->cb_user);                      // decode.rs:107
@@ -227,7 +322,7 @@ int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int 
     const uint64_t alen = rows * p.row;
     const uint64_t nout = polyphase_len(alen, p.last.l, p.last.m, 1);
     Prof pr(d, "final_resample");
-    APT_TRY(launch_polyphase(c, d->d_f, APT_F32, alen, d->d_one, p.last.l, p.last.m, 0, nout, false, 0.f, 1.f, rows_out));
+    APT_TRY(launch_polyphase(c, d->d_f, APT_F32, alen, d->d_one, p.last.l, p.last.m, 0, 0, nout, false, 0.f, 1.f, rows_out));
     d->job_fixed_out = nout;
     return APT_OK;
 }

@@ -63,6 +63,14 @@ struct apt_decoder {
     aptb200::u32 *d_tile_xs = nullptr;
     int8_t *d_guard = nullptr;
     void *d_in = nullptr;          // staging for submit_host (f32 sized)
+    float *d_conv = nullptr;       // f32 copy of a PCM16 input for the tiled resampler (allocated on first use)
+    // chunked upload of long host recordings (BASELINE configs[2]): two staging buffers of chunk_samples each,
+    // a copy stream and events so that the H2D of chunk c+1 overlaps the resampling of chunk c
+    uint64_t chunk_samples = 0;    // 0: the whole recording is staged at once
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    uint64_t job_chunks = 0;
+    uint64_t conv_cap = 0;         // samples d_conv holds
     float *d_r = nullptr;          // resampled signal, only for the L == 1 first stage
     float *d_e = nullptr;          // envelope           ("demodulation_result")
     float *d_f = nullptr;          // low-passed         ("filter_result")

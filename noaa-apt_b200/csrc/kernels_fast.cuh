@@ -120,8 +120,10 @@ constexpr int kWsEpilogueWarps = 6;
 template <bool ENVELOPE>
 __global__ void __launch_bounds__(32 * (13 + kWsEpilogueWarps + 1), 1)
 k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restrict__ tile_taps,
-               const u32 *__restrict__ group_xs, TilePlan tp, u64 nout, u64 ntiles, float cosphi2, float sinphi,
-               float *__restrict__ out, unsigned long long *__restrict__ prof) {
+               const u32 *__restrict__ group_xs, TilePlan tp, u64 nout, u64 tile_begin, u64 ntiles, float cosphi2,
+               float sinphi, float *__restrict__ out, unsigned long long *__restrict__ prof) {
+    // tiles [tile_begin, ntiles) are computed; `signal` may be a biased pointer into a chunk buffer (signal + x is
+    // valid for every sample x those tiles touch), `len` is always the length of the whole signal
     constexpr int Q = kTileQ, KS = kTileKS, QT = kTileQT, E = kWsEpilogueWarps;
     // optional phase timing (APTB200_TILE_PROFILE): cycles summed over the tiles of CTA 0, lane 0 of one warp per role
     const bool profiling = prof != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
@@ -171,7 +173,7 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
                              reinterpret_cast<const unsigned char *>(tile_taps) + done, min(total - done, 32768u), bar_taps);
         }
         u32 n = 0;
-        for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+        for (u64 tile = tile_begin + blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
             const u32 st = n & 1;
             float *rows = s_stage0 + st * tp.stage_floats;
             float *vrow = rows + tp.rows_floats;
@@ -263,7 +265,7 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
         float *plane_dst = s_planes + ks * plane_floats + ql * tp.plane_pitch + warp * kTileR;
         mbar_wait(bar_taps, 0);
         u32 n = 0;
-        for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+        for (u64 tile = tile_begin + blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
             const u32 st = n & 1;
             const float *rows = s_stage0 + st * tp.stage_floats;
             PROF_MARK();
@@ -348,7 +350,7 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
         const float inv_sinphi = 1.f / sinphi;
         const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
         u32 n = 0;
-        for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+        for (u64 tile = tile_begin + blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
             const u64 k_base = tile * tile_out;
             const bool full_tile = k_base + tile_out <= nout && out_aligned;
             float *out_tile = out + k_base;

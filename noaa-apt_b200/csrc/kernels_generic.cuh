@@ -59,9 +59,10 @@ __device__ __forceinline__ float polyphase_dot(const InT *__restrict__ signal, u
 template <typename InT, bool ENVELOPE>
 __global__ void __launch_bounds__(256)
 k_polyphase_generic(const InT *__restrict__ signal, u64 len, const float *__restrict__ h, u32 l, u32 m,
-                    u64 off2, u64 nout, float cosphi2, float sinphi, float *__restrict__ out) {
+                    u64 off2, u64 k_begin, u64 nout, float cosphi2, float sinphi, float *__restrict__ out) {
+    // outputs [k_begin, nout); `signal` may be a biased pointer into a chunk buffer, `len` is the whole signal's length
     __shared__ float r[257];
-    for (u64 k0 = static_cast<u64>(blockIdx.x) * 256; k0 < nout; k0 += static_cast<u64>(gridDim.x) * 256) {
+    for (u64 k0 = k_begin + static_cast<u64>(blockIdx.x) * 256; k0 < nout; k0 += static_cast<u64>(gridDim.x) * 256) {
         const u64 k = k0 + threadIdx.x;
         float v = 0.f;
         if (k < nout) v = polyphase_dot(signal, len, h, l, m, off2, k);
@@ -75,6 +76,24 @@ k_polyphase_generic(const InT *__restrict__ signal, u64 len, const float *__rest
         if (k < nout) out[k] = k == 0 ? 0.f : envelope2(r[threadIdx.x], r[threadIdx.x + 1], cosphi2, sinphi);
         __syncthreads();
     }
+}
+
+// wav.rs:37 as a kernel: PCM16 -> f32 (`as f32`), 8 samples per thread (16-byte load, two 16-byte stores).
+// Feeds the tiled resampler when the caller hands over the WAV's int16 samples (halves the PCIe bytes).
+__global__ void __launch_bounds__(256)
+k_pcm16_to_f32(const int16_t *__restrict__ in, u64 n, float *__restrict__ out) {
+    const u64 n8 = n / 8;
+    for (u64 i = static_cast<u64>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<u64>(gridDim.x) * blockDim.x) {
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(in) + i);
+        float4 a, b;
+        a.x = static_cast<float>(static_cast<short>(v.x & 0xffff)); a.y = static_cast<float>(v.x >> 16);
+        a.z = static_cast<float>(static_cast<short>(v.y & 0xffff)); a.w = static_cast<float>(v.y >> 16);
+        b.x = static_cast<float>(static_cast<short>(v.z & 0xffff)); b.y = static_cast<float>(v.z >> 16);
+        b.z = static_cast<float>(static_cast<short>(v.w & 0xffff)); b.w = static_cast<float>(v.w >> 16);
+        reinterpret_cast<float4 *>(out)[2 * i] = a;
+        reinterpret_cast<float4 *>(out)[2 * i + 1] = b;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n - n8 * 8) out[n8 * 8 + threadIdx.x] = static_cast<float>(in[n8 * 8 + threadIdx.x]);
 }
 
 // demodulate alone (stage entry point, and the L == 1 decode path).

@@ -37,30 +37,31 @@ int roots_with_chunk(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist,
 }  // namespace
 
 int launch_polyphase(const LaunchCtx &c, const void *signal, int format, u64 len, const float *taps, u32 l, u32 m,
-                     u64 off2, u64 nout, bool envelope, float cosphi2, float sinphi, float *out) {
-    if (nout == 0) return APT_OK;
-    const unsigned grid = grid_for(nout, 256, c.sm_count);
+                     u64 off2, u64 k_begin, u64 nout, bool envelope, float cosphi2, float sinphi, float *out) {
+    if (nout <= k_begin) return APT_OK;
+    const unsigned grid = grid_for(nout - k_begin, 256, c.sm_count);
     if (format == APT_PCM16) {
         const int16_t *s = static_cast<const int16_t *>(signal);
-        if (envelope) k_polyphase_generic<int16_t, true><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, nout, cosphi2, sinphi, out);
-        else k_polyphase_generic<int16_t, false><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, nout, cosphi2, sinphi, out);
+        if (envelope) k_polyphase_generic<int16_t, true><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, k_begin, nout, cosphi2, sinphi, out);
+        else k_polyphase_generic<int16_t, false><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, k_begin, nout, cosphi2, sinphi, out);
     } else {
         const float *s = static_cast<const float *>(signal);
-        if (envelope) k_polyphase_generic<float, true><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, nout, cosphi2, sinphi, out);
-        else k_polyphase_generic<float, false><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, nout, cosphi2, sinphi, out);
+        if (envelope) k_polyphase_generic<float, true><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, k_begin, nout, cosphi2, sinphi, out);
+        else k_polyphase_generic<float, false><<<grid, 256, 0, c.stream>>>(s, len, taps, l, m, off2, k_begin, nout, cosphi2, sinphi, out);
     }
     APT_CUDA(cudaGetLastError());
     return APT_OK;
 }
 
-int launch_polyphase_tiled(const LaunchCtx &c, const float *signal, u64 len, const float *raw_taps,
-                           const float *tile_taps, const u32 *group_xs, const TilePlan &tp, u64 nout, bool envelope,
-                           float cosphi2, float sinphi, float *out) {
-    (void)raw_taps;
+int launch_polyphase_tiled(const LaunchCtx &c, const float *signal, u64 len, const float *tile_taps,
+                           const u32 *group_xs, const TilePlan &tp, u64 nout, u64 tile_begin, u64 tile_end,
+                           bool envelope, float cosphi2, float sinphi, float *out) {
     if (nout == 0) return APT_OK;
     const u64 tile_out = static_cast<u64>(tp.qt) * tp.p_out;
-    const u64 ntiles = (nout + tile_out - 1) / tile_out;
-    const unsigned grid = static_cast<unsigned>(std::min<u64>(ntiles, static_cast<u64>(c.sm_count)));
+    u64 ntiles = (nout + tile_out - 1) / tile_out;
+    if (tile_end != 0) ntiles = std::min(ntiles, tile_end);
+    if (tile_begin >= ntiles) return APT_OK;
+    const unsigned grid = static_cast<unsigned>(std::min<u64>(ntiles - tile_begin, static_cast<u64>(c.sm_count)));
     const unsigned block = 32 * (tp.groups + kWsEpilogueWarps + 1);   // compute + epilogue + producer warps
     unsigned long long *prof = nullptr;
     if (getenv("APTB200_TILE_PROFILE")) {
@@ -70,13 +71,13 @@ int launch_polyphase_tiled(const LaunchCtx &c, const float *signal, u64 len, con
     if (envelope) {
         auto kern = k_polyphase_ws<true>;
         APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem_bytes)));
-        kern<<<grid, block, tp.smem_bytes, c.stream>>>(signal, len, tile_taps, group_xs, tp, nout, ntiles, cosphi2,
-                                                        sinphi, out, prof);
+        kern<<<grid, block, tp.smem_bytes, c.stream>>>(signal, len, tile_taps, group_xs, tp, nout, tile_begin, ntiles,
+                                                        cosphi2, sinphi, out, prof);
     } else {
         auto kern = k_polyphase_ws<false>;
         APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tp.smem_bytes)));
-        kern<<<grid, block, tp.smem_bytes, c.stream>>>(signal, len, tile_taps, group_xs, tp, nout, ntiles, cosphi2,
-                                                        sinphi, out, prof);
+        kern<<<grid, block, tp.smem_bytes, c.stream>>>(signal, len, tile_taps, group_xs, tp, nout, tile_begin, ntiles,
+                                                        cosphi2, sinphi, out, prof);
     }
     APT_CUDA(cudaGetLastError());
     if (prof) {
@@ -104,6 +105,13 @@ int launch_fir_decimate(const LaunchCtx &c, const void *signal, int format, cons
         k_fir_decimate_generic<int16_t><<<grid, 256, 0, c.stream>>>(static_cast<const int16_t *>(signal), coeff, ntaps, m, nout, out);
     else
         k_fir_decimate_generic<float><<<grid, 256, 0, c.stream>>>(static_cast<const float *>(signal), coeff, ntaps, m, nout, out);
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+int launch_pcm16_to_f32(const LaunchCtx &c, const int16_t *in, u64 n, float *out) {
+    if (n == 0) return APT_OK;
+    k_pcm16_to_f32<<<grid_for(n / 8 + 1, 256, c.sm_count), 256, 0, c.stream>>>(in, n, out);
     APT_CUDA(cudaGetLastError());
     return APT_OK;
 }

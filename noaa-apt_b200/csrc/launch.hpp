@@ -65,8 +65,11 @@ struct LaunchCtx {
 
 // fast_resampling (dsp.rs:186-289), optionally fused with demodulate (dsp.rs:350-383).
 // format: APT_F32 / APT_PCM16 samples.
+// Outputs [k_begin, k_end) only (k_end <= total outputs); `signal` is the address sample 0 would have.
 int launch_polyphase(const LaunchCtx &c, const void *signal, int format, u64 len, const float *taps, u32 l, u32 m,
-                     u64 off2, u64 nout, bool envelope, float cosphi2, float sinphi, float *out);
+                     u64 off2, u64 k_begin, u64 k_end, bool envelope, float cosphi2, float sinphi, float *out);
+// wav.rs:37: PCM16 -> f32 (both pointers 16-byte aligned).
+int launch_pcm16_to_f32(const LaunchCtx &c, const int16_t *in, u64 n, float *out);
 // dsp::filter + decimate (dsp.rs:396-404, 299-303).
 int launch_fir_decimate(const LaunchCtx &c, const void *signal, int format, const float *coeff, u32 ntaps, u32 m,
                         u64 nout, float *out);
@@ -98,8 +101,9 @@ int launch_gather(const LaunchCtx &c, const float *f, const u32 *positions, cons
 bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, std::vector<float> &tile_taps,
                     std::vector<u32> &group_xs);
 // Tiled fast_resampling (+ envelope).  f32 samples only.
-int launch_polyphase_tiled(const LaunchCtx &c, const float *signal, u64 len, const float *raw_taps,
-                           const float *tile_taps, const u32 *group_xs, const TilePlan &tp, u64 nout, bool envelope,
-                           float cosphi2, float sinphi, float *out);
+// Tiles [tile_begin, tile_end) (tile_end == 0: all); `signal` is the address sample 0 would have.
+int launch_polyphase_tiled(const LaunchCtx &c, const float *signal, u64 len, const float *tile_taps,
+                           const u32 *group_xs, const TilePlan &tp, u64 nout, u64 tile_begin, u64 tile_end,
+                           bool envelope, float cosphi2, float sinphi, float *out);
 
 }  // namespace aptb200

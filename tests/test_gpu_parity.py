@@ -301,3 +301,25 @@ def test_parallel_and_sequential_picker_agree(monkeypatch):
     seq = na.find_sync(na.Context(), f, 12480)
     assert np.array_equal(par, st["sync_pos"])
     assert np.array_equal(seq, st["sync_pos"])
+
+
+@pytest.mark.parametrize("rate", [48000, 11025])
+def test_chunked_upload_of_long_recordings(rate, monkeypatch):
+    """BASELINE configs[2] in miniature: a recording longer than the staging chunk is uploaded in chunks with the
+    filter-length overlap while the previous chunk is resampled; the result must not depend on the chunking."""
+    pcm = synth.apt_pcm16(rate, 20, seed=31)
+    x = pcm.astype(np.float32)
+    ref, st = oracle.decode_steps(x, rate)
+    with na.Decoder(rate, na.Settings(), max_samples=x.size) as dec:
+        whole = dec.decode(x)
+        whole_env = dec.read_stage("demodulated")
+    monkeypatch.setenv("APTB200_CHUNK_SAMPLES", "150000")
+    with na.Decoder(rate, na.Settings(), max_samples=x.size) as dec:
+        got = dec.decode(x)
+        env = dec.read_stage("demodulated")
+        assert np.array_equal(dec.last_sync(), st["sync_pos"])
+        got16 = dec.decode(pcm)
+    assert np.array_equal(env, whole_env)          # same kernels, same tiles: bit-identical to the one-shot upload
+    assert np.array_equal(got, whole)
+    assert got.size == ref.size and nerr(got, ref) <= TOL
+    assert got16.size == ref.size and nerr(got16, ref) <= TOL
