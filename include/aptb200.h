@@ -219,7 +219,7 @@ int apt_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
  * group_xs (groups entries: first input sample of each group relative to its row). */
 typedef struct apt_tile_info {
     uint32_t usable, groups, p_out, p_in, usteps, row_len, rows_per_tile, smem_bytes, slices, slice_stride,
-        half_taps, shift, iters, group_stride, ctas_per_sm, pair_pitch;
+        half_taps, shift, iters, group_stride, ctas_per_sm, pair_pitch, halves, rows_per_copy;
 } apt_tile_info;
 int apt_tile_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_tile_info *info,
                   float *tile_taps, size_t cap_taps, uint32_t *group_xs, size_t cap_groups);

@@ -47,7 +47,7 @@ class CFilter(C.Structure):
 class CTileInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("usable", "groups", "p_out", "p_in", "usteps", "row_len", "rows_per_tile",
                                           "smem_bytes", "slices", "slice_stride", "half_taps", "shift", "iters",
-                                          "group_stride", "ctas_per_sm", "pair_pitch")]
+                                          "group_stride", "ctas_per_sm", "pair_pitch", "halves", "rows_per_copy")]
 
 
 STATUS_CB = C.CFUNCTYPE(None, C.c_float, C.c_char_p, C.c_void_p)

@@ -738,7 +738,7 @@ extern "C" int apt_tile_plan(uint32_t l, uint32_t m, const float *taps, size_t n
     if (!make_tile_plan(l, m, h, tp, tt, xs)) return APT_OK;
     *info = apt_tile_info{1, tp.groups, tp.p_out, tp.p_in, tp.usteps, tp.row_len, tp.qt, tp.smem_bytes, 4,
                           tp.slice_stride, tp.half_taps, tp.shift, tp.iters, tp.group_stride, tp.ctas_per_sm,
-                          tp.pair_pitch};
+                          tp.pair_pitch, tp.halves, tp.rows_per_copy};
     if (tile_taps) memcpy(tile_taps, tt.data(), std::min(cap_taps, tt.size()) * sizeof(float));
     if (group_xs) memcpy(group_xs, xs.data(), std::min(cap_groups, xs.size()) * sizeof(u32));
     return APT_OK;

@@ -191,15 +191,16 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
                 // exists (a multiple of 4 floats) comes by TMA; the rest -- the last <4 samples and everything
                 // past the end of the signal, which reads as zero (signal.get(x) == None, dsp.rs:257) -- by this
                 // warp's own stores.  Interior tiles are pure TMA.
-                const u32 pair_len = tp.p_in + tp.row_len;
+                const u32 rpc = tp.rows_per_copy, ncopies = QT / rpc;
+                const u32 pair_len = (rpc - 1) * tp.p_in + tp.row_len;
                 const u64 halo_end = x_halo + tp.usteps;
                 const bool edge = x_end > len || (want_halo && halo_end > len);
                 auto valid_of = [&](u64 x0, u32 nfl) -> u32 {
                     return x0 >= len ? 0u : static_cast<u32>(min(static_cast<u64>(nfl), len - x0));
                 };
                 if (edge) {
-                    for (u32 i = 0; i < QT / 2; ++i) {
-                        const u64 xr = x_base + static_cast<u64>(2 * i) * tp.p_in;
+                    for (u32 i = 0; i < ncopies; ++i) {
+                        const u64 xr = x_base + static_cast<u64>(rpc * i) * tp.p_in;
                         const u32 valid = valid_of(xr, pair_len);
                         for (u32 c = (valid & ~3u) + lane; c < pair_len; c += 32)
                             rows[i * tp.pair_pitch + c] = c < valid ? __ldg(signal + xr + c) : 0.f;
@@ -214,18 +215,18 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
                 if (lane == 0) {
                     fence_proxy_async();          // the stage was last read through the generic proxy
                     if (!edge) {
-                        mbar_expect_tx(full_rows + st, ((QT / 2) * pair_len + (want_halo ? tp.usteps : 0)) * 4);
-                        for (u32 i = 0; i < QT / 2; ++i)
-                            tma_bulk_g2s(rows + i * tp.pair_pitch, signal + x_base + static_cast<u64>(2 * i) * tp.p_in,
+                        mbar_expect_tx(full_rows + st, (ncopies * pair_len + (want_halo ? tp.usteps : 0)) * 4);
+                        for (u32 i = 0; i < ncopies; ++i)
+                            tma_bulk_g2s(rows + i * tp.pair_pitch, signal + x_base + static_cast<u64>(rpc * i) * tp.p_in,
                                          pair_len * 4, full_rows + st);
                         if (want_halo) tma_bulk_g2s(vrow, signal + x_halo, tp.usteps * 4, full_rows + st);
                     } else {
                         u32 tx_floats = want_halo ? (valid_of(x_halo, tp.usteps) & ~3u) : 0u;
-                        for (u32 i = 0; i < QT / 2; ++i)
-                            tx_floats += valid_of(x_base + static_cast<u64>(2 * i) * tp.p_in, pair_len) & ~3u;
+                        for (u32 i = 0; i < ncopies; ++i)
+                            tx_floats += valid_of(x_base + static_cast<u64>(rpc * i) * tp.p_in, pair_len) & ~3u;
                         mbar_expect_tx(full_rows + st, tx_floats * 4);
-                        for (u32 i = 0; i < QT / 2; ++i) {
-                            const u64 xr = x_base + static_cast<u64>(2 * i) * tp.p_in;
+                        for (u32 i = 0; i < ncopies; ++i) {
+                            const u64 xr = x_base + static_cast<u64>(rpc * i) * tp.p_in;
                             const u32 nfl = valid_of(xr, pair_len) & ~3u;
                             if (nfl) tma_bulk_g2s(rows + i * tp.pair_pitch, signal + xr, nfl * 4, full_rows + st);
                         }
@@ -237,10 +238,11 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
                 }
             } else {
                 // unaligned signal pointer: the warp fills the whole stage itself (slow, correct)
-                const u32 pair_len = tp.p_in + tp.row_len;
-                for (u32 i = 0; i < QT / 2; ++i)
+                const u32 rpc = tp.rows_per_copy;
+                const u32 pair_len = (rpc - 1) * tp.p_in + tp.row_len;
+                for (u32 i = 0; i < QT / rpc; ++i)
                     for (u32 c = lane; c < pair_len; c += 32) {
-                        const u64 x = x_base + static_cast<u64>(2 * i) * tp.p_in + c;
+                        const u64 x = x_base + static_cast<u64>(rpc * i) * tp.p_in + c;
                         rows[i * tp.pair_pitch + c] = x < len ? __ldg(signal + x) : 0.f;
                     }
                 if (want_halo)
@@ -256,13 +258,16 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
         const u32 ks = lane >> 3, ql = lane & 7;
         const u32 w0 = group_xs[warp];
         const u32 it_a_end = tp.half_taps / 16;       // half A is active for iterations [0, it_a_end)
-        const u32 it_b_begin = tp.shift / 16;         // half B for [it_b_begin, iters)
+        const u32 it_b_begin = tp.halves == 2 ? tp.shift / 16 : tp.iters;   // half B for [it_b_begin, iters)
+        const u32 rec_bytes = tp.halves * 64;         // one (iteration, slice lane) tap record
+        const u32 R = 4 * tp.halves;
         const u32 tap_base = smem_u32(s_taps) + (warp * tp.group_stride + ks * tp.slice_stride) * 4;
         // row r lives at pair r/2, half r%2; this thread reads rows ql, ql+8, ql+16, ql+24
-        const u32 row_off = ((ql >> 1) * tp.pair_pitch + (ql & 1) * tp.p_in + w0 + ks * 4) * 4;
-        const u32 row_step8 = 4 * tp.pair_pitch * 4;
+        const u32 row_off = (tp.rows_per_copy == 2 ? (ql >> 1) * tp.pair_pitch + (ql & 1) * tp.p_in : ql * tp.pair_pitch) * 4 +
+                            (w0 + ks * 4) * 4;
+        const u32 row_step8 = (8 / tp.rows_per_copy) * tp.pair_pitch * 4;
         const u32 plane_floats = QT * tp.plane_pitch;
-        float *plane_dst = s_planes + ks * plane_floats + ql * tp.plane_pitch + warp * kTileR;
+        float *plane_dst = s_planes + ks * plane_floats + ql * tp.plane_pitch + warp * R;
         mbar_wait(bar_taps, 0);
         u32 n = 0;
         for (u64 tile = tile_begin + blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
@@ -286,7 +291,7 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
                     for (int j = 0; j < Q; ++j) s[j] = lds128(row_addr + j * row_step8);
                     half_fma2(acc_a, tap_addr, s);
                     row_addr += KS * 16;
-                    tap_addr += 128;
+                    tap_addr += rec_bytes;
                 }
                 for (; it < it_a_end; ++it) {                          // both halves
                     float4 s[Q];
@@ -295,7 +300,7 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
                     half_fma2(acc_a, tap_addr, s);
                     half_fma2(acc_b, tap_addr + 64, s);
                     row_addr += KS * 16;
-                    tap_addr += 128;
+                    tap_addr += rec_bytes;
                 }
                 for (; it < tp.iters; ++it) {                          // half B only
                     float4 s[Q];
@@ -303,17 +308,20 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
                     for (int j = 0; j < Q; ++j) s[j] = lds128(row_addr + j * row_step8);
                     half_fma2(acc_b, tap_addr + 64, s);
                     row_addr += KS * 16;
-                    tap_addr += 128;
+                    tap_addr += rec_bytes;
                 }
             }
-            // r[K0 - 1]: output 7 (half B, r = 3) of the last group, applied to the halo row
+            // r[K0 - 1]: the last output of the last group, applied to the halo row
             float halo = 0.f;
             if (ENVELOPE && warp == G - 1 && tile > 0) {
                 const float *vrow = rows + tp.rows_floats;
                 const float *tg = s_taps + static_cast<size_t>(G - 1) * tp.group_stride;
-                for (u32 u = tp.shift + lane; u < tp.usteps; u += 32) {
+                // the group's last output: r = 3 of half B (two halves) or of half A (one)
+                const u32 rec = 16 * tp.halves, off = tp.halves == 2 ? 16 + 3 : 3;
+                const u32 ubeg = tp.halves == 2 ? tp.shift : 0, uend = tp.halves == 2 ? tp.usteps : tp.half_taps;
+                for (u32 u = ubeg + lane; u < uend; u += 32) {
                     const u32 chunk = u >> 2, uu = u & 3;            // chunk = it*KS + ks
-                    halo = fmaf(tg[(chunk & 3) * tp.slice_stride + (chunk >> 2) * 32 + 16 + uu * 4 + 3], vrow[u], halo);
+                    halo = fmaf(tg[(chunk & 3) * tp.slice_stride + (chunk >> 2) * rec + off + uu * 4], vrow[u], halo);
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) halo += __shfl_xor_sync(0xffffffffu, halo, o);
@@ -333,7 +341,7 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
                 unpack2(acc_b[1][j], vb.z, vb.w);
                 float *dst = plane_dst + 8 * j * tp.plane_pitch;
                 *reinterpret_cast<float4 *>(dst) = va;
-                *reinterpret_cast<float4 *>(dst + 4) = vb;
+                if (tp.halves == 2) *reinterpret_cast<float4 *>(dst + 4) = vb;
             }
             if (ENVELOPE && warp == G - 1 && lane == 0) *s_halo = halo;
             __syncwarp();
@@ -375,7 +383,7 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
                     float4 res = cur;
                     if (ENVELOPE) {
                         // previous output: left neighbour, last output of the previous row, or the halo for kl == 0
-                        const float *pc = kl == 0 ? cell : c4 > 0 ? cell - 1 : cell - 5;
+                        const float *pc = kl == 0 ? cell : c4 > 0 ? cell - 1 : cell - (tp.plane_pitch - tp.p_out) - 1;
                         float prev = (pc[0] + pc[plane_floats]) + (pc[2 * plane_floats] + pc[3 * plane_floats]);
                         if (kl == 0) prev = *s_halo;
                         res.x = envelope2_fast(prev, cur.x, cosphi2, inv_sinphi);

@@ -37,14 +37,16 @@ struct PickScratch {
 // Geometry of the tiled kernel for one (L, M, taps) triple; built on the host (make_tile_plan).
 struct TilePlan {
     u32 l, m;          // resampling ratio
-    u32 groups;        // G = L / gcd(8, L)  (= warps per CTA); group g owns outputs 8g..8g+7 of a super-period
+    u32 halves;        // 2: groups of 8 outputs in two half windows; 1: groups of 4 outputs (one window)
+    u32 groups;        // G = L / gcd(R, L), R = 4*halves (= compute warps per CTA); group g owns outputs R*g..R*g+R-1
     u32 p_out, p_in;   // outputs / inputs per super-period (p_out = 8G)
     u32 usteps;        // samples a group reads per row (= half_taps + shift), multiple of 16
     u32 half_taps;     // padded taps of one half (4 outputs), multiple of 16
     u32 shift;         // half B's window starts this many samples after half A's (multiple of 16)
     u32 iters;         // loop iterations = usteps / 16
     u32 row_len;       // samples of one row the kernel may touch (multiple of 4)
-    u32 pair_pitch;    // floats between consecutive row pairs in shared memory (rows 2i, 2i+1 share one bulk copy)
+    u32 pair_pitch;    // floats between consecutive copies in shared memory
+    u32 rows_per_copy; // 2: rows 2i, 2i+1 share one bulk copy (they overlap in the signal); 1: one copy per row
     u32 rows_floats;   // floats of the rows of one stage (qt * row_len)
     u32 plane_pitch;   // floats per row of a partial-sum plane (p_out + 4)
     u32 vec_magic;     // (v * vec_magic) >> 16 == v / (p_out/4) for every v < qt*p_out/4

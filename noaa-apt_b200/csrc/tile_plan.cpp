@@ -8,15 +8,17 @@
 namespace aptb200 {
 
 namespace {
-constexpr u32 kR = 8, kH = 4, kQ = 4, kKS = 4, kQT = (32 / kKS) * kQ;
+constexpr u32 kH = 4, kQ = 4, kKS = 4, kQT = (32 / kKS) * kQ;
 constexpr u32 kMaxGroups = 13;                 // warps per CTA the kernel is compiled for (416 threads)
 constexpr u32 kSmemTwoCtas = (233472 - 2 * 1024) / 2 - 512;   // dynamic bytes that still let two CTAs share an SM
 constexpr u32 kSmemOneCta = 227 * 1024;
 constexpr u32 kIterSamples = 4 * kKS;          // samples consumed per loop iteration (one 16-byte chunk per slice lane)
 }  // namespace
 
-bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, std::vector<float> &tile_taps,
-                    std::vector<u32> &group_xs) {
+// One attempt with R = 4*halves outputs per group (halves = 2: two half windows per group; 1: a single one).
+static bool try_tile_plan(u32 halves, u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp,
+                          std::vector<float> &tile_taps, std::vector<u32> &group_xs) {
+    const u32 kR = kH * halves;
     if (l < 2 || m == 0 || taps.empty()) return false;
     const u64 off2 = 2 * ((static_cast<u64>(taps.size()) - 1) / 2);
     const u32 groups = l / std::gcd(kR, l);
@@ -30,12 +32,13 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
     auto first_x = [&](u64 k) { return (k * m + l - 1) / l; };          // first sample output k touches
     auto last_x = [&](u64 k) { return (k * m + off2) / l; };            // last one
     u64 d_min = ~0ull, d_max = 0;
-    for (u32 g = 0; g < groups; ++g) {
+    for (u32 g = 0; g < groups && halves == 2; ++g) {
         const u64 k0 = static_cast<u64>(kR) * g;
         const u64 d = first_x(k0 + kH) - first_x(k0);
         d_min = std::min(d_min, d);
         d_max = std::max(d_max, d);
     }
+    if (halves == 1) d_min = d_max = 0;
     // Candidate shifts (multiples of one loop iteration).  A larger shift than the smallest spacing is fine
     // as long as every group's window start is pulled back far enough for half B to still see its first tap.
     u64 shift = 0, ua = 0, max_w0 = 0;
@@ -47,11 +50,12 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
         bool ok = true;
         for (u32 g = 0; g < groups && ok; ++g) {
             const u64 k0 = static_cast<u64>(kR) * g;
-            if (first_x(k0 + kH) < cand) { ok = false; break; }
-            const u64 w0 = std::min(first_x(k0), first_x(k0 + kH) - cand) & ~static_cast<u64>(3);   // 16-byte aligned
+            if (halves == 2 && first_x(k0 + kH) < cand) { ok = false; break; }
+            const u64 w0 = (halves == 2 ? std::min(first_x(k0), first_x(k0 + kH) - cand) : first_x(k0)) &
+                           ~static_cast<u64>(3);                                // 16-byte aligned
             xs[g] = static_cast<u32>(w0);
             need = std::max(need, last_x(k0 + kH - 1) - w0 + 1);               // half A relative to w0
-            need = std::max(need, last_x(k0 + kR - 1) - (w0 + cand) + 1);      // half B relative to w0 + shift
+            if (halves == 2) need = std::max(need, last_x(k0 + kR - 1) - (w0 + cand) + 1);   // half B relative to w0 + shift
             mw = std::max(mw, w0);
         }
         if (!ok) continue;
@@ -72,27 +76,39 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
     // (rows r = 0..7: pair r/2, half r%2) start in 8 different 16-byte bank groups -> conflict-free LDS.128.
     const u64 row_len = (max_w0 + span + 3) / 4 * 4;     // samples of one row the kernel may touch
     u64 pair_pitch = p_in + row_len;
+    u32 rows_per_copy = 2;
     for (;; pair_pitch += 4) {
         u32 seen = 0;
         for (u32 r = 0; r < 8; ++r) seen |= 1u << (((r >> 1) * (pair_pitch / 4) + (r & 1) * (p_in / 4)) % 8);
         if (seen == 0xFF) break;
-        if (pair_pitch > p_in + row_len + 64) return false;
+        if (pair_pitch > p_in + row_len + 64) {
+            // no skew separates the 8 row lanes for this p_in: one bulk copy per row, odd pitch in 16-byte units
+            rows_per_copy = 1;
+            pair_pitch = row_len;
+            if ((pair_pitch / 4) % 2 == 0) pair_pitch += 4;
+            break;
+        }
     }
 
     // Tap table [group][slice lane][iteration][32]: 16 floats for half A (4 samples x 4 outputs), 16 for half B.
     // Each slice lane's sub-table is followed by 8 floats of padding, which skews the four slice lanes of a
     // warp onto different 16-byte bank groups (sub-table stride/4 = 2 mod 8).
-    const u64 rec = 2 * 4 * kH;                          // 32 floats per (iteration, slice lane)
-    const u64 lane_stride = iters * rec + 8;             // floats between the sub-tables of one group
+    const u64 rec = halves * 4 * kH;                     // 16 floats per half per (iteration, slice lane)
+    u64 lane_stride = iters * rec + 8;                   // floats between the sub-tables of one group
+    for (;; lane_stride += 4) {                          // the 4 slice lanes must start in 4 different bank groups
+        u32 seen = 0;
+        for (u32 ks = 0; ks < kKS; ++ks) seen |= 1u << ((ks * (lane_stride / 4)) % 8);
+        if (__builtin_popcount(seen) == static_cast<int>(kKS)) break;
+    }
     const u64 group_stride = kKS * lane_stride;
-    const u64 plane_pitch = p_out + 4;                   // partial-sum planes [slice][row][p_out + 4]
-    const u64 rows_floats = static_cast<u64>(kQT / 2) * pair_pitch;
+    u64 plane_pitch = p_out + 4;                         // partial-sum planes [slice][row][plane_pitch]
+    if ((plane_pitch / 4) % 2 == 0) plane_pitch += 4;    // odd in 16-byte units: conflict-free float4 stores
+    const u64 rows_floats = static_cast<u64>(kQT / rows_per_copy) * pair_pitch;
     // warp-specialised kernel: barriers + taps + 2 row stages (each with its halo row) + partial-sum planes
     const u64 stage_floats = rows_floats + span;
     const u64 planes_floats = kKS * static_cast<u64>(kQT) * plane_pitch;
     const u64 smem = 128 + (groups * group_stride + 2 * stage_floats + planes_floats) * 4;
     if (smem > kSmemOneCta) return false;
-    if ((plane_pitch / 4) % 2 == 0) return false;        // p_out/4 must be even (8 | p_out): always true
 
     tile_taps.assign(groups * group_stride, 0.f);
     auto tap_at = [&](long long idx) -> float {
@@ -109,8 +125,9 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
                     for (u32 r = 0; r < kH; ++r) {
                         // half A sees sample u as its tap u; half B (window starts `shift` later) likewise
                         dst[uu * kH + r] = u < ua ? tap_at(x * l - static_cast<long long>((k0 + r) * m)) : 0.f;
-                        dst[16 + uu * kH + r] =
-                            u >= shift ? tap_at(x * l - static_cast<long long>((k0 + kH + r) * m)) : 0.f;
+                        if (halves == 2)
+                            dst[16 + uu * kH + r] =
+                                u >= shift ? tap_at(x * l - static_cast<long long>((k0 + kH + r) * m)) : 0.f;
                     }
                 }
             }
@@ -127,8 +144,10 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
     tp.iters = static_cast<u32>(iters);
     tp.row_len = static_cast<u32>(row_len);
     tp.pair_pitch = static_cast<u32>(pair_pitch);
+    tp.rows_per_copy = rows_per_copy;
     tp.rows_floats = static_cast<u32>(rows_floats);
     tp.plane_pitch = static_cast<u32>(plane_pitch);
+    tp.halves = halves;
     tp.qt = kQT;
     {
         const u32 vpr = static_cast<u32>(p_out / 4), nvec = kQT * vpr;
@@ -145,6 +164,13 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
     tp.debug = 0;
     if (const char *e = getenv("APTB200_TILE_DEBUG")) tp.debug = static_cast<u32>(atoi(e));
     return true;
+}
+
+bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, std::vector<float> &tile_taps,
+                    std::vector<u32> &group_xs) {
+    // 8 outputs per group when it fits shared memory, else 4 (96 kHz input, the slow profile)
+    if (try_tile_plan(2, l, m, taps, tp, tile_taps, group_xs)) return true;
+    return try_tile_plan(1, l, m, taps, tp, tile_taps, group_xs);
 }
 
 }  // namespace aptb200

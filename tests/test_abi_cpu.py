@@ -152,35 +152,47 @@ def _tile_plan(na, l, m, taps):
     xs = np.zeros(info.groups, np.uint32)
     assert lib.apt_tile_plan(l, m, taps.ctypes.data, taps.size, C.byref(info), tt.ctypes.data, tt.size,
                              xs.ctypes.data, xs.size) == 0
-    # [g][slice lane][iteration][32] (+8 floats of padding per sub-table); chunk = iteration*slices + lane
-    rec = tt.reshape(info.groups, info.slices, info.slice_stride)[:, :, : info.iters * 32]
-    rec = rec.reshape(info.groups, info.slices, info.iters, 32).transpose(0, 2, 1, 3)   # -> [g][it][lane][32]
-    rec = rec.reshape(info.groups, info.iters * info.slices, 32)                         # [g][chunk][32]
+    # [g][slice lane][iteration][16*halves] (+ padding per sub-table); chunk = iteration*slices + lane
+    rl = 16 * info.halves
+    rec = tt.reshape(info.groups, info.slices, info.slice_stride)[:, :, : info.iters * rl]
+    rec = rec.reshape(info.groups, info.slices, info.iters, rl).transpose(0, 2, 1, 3)   # -> [g][it][lane][rl]
+    rec = rec.reshape(info.groups, info.iters * info.slices, rl)                         # [g][chunk][rl]
     ta = rec[:, :, 0:16].reshape(info.groups, info.usteps, 4)                      # [g][u][r]
-    tb = rec[:, :, 16:32].reshape(info.groups, info.usteps, 4)
+    tb = rec[:, :, 16:32].reshape(info.groups, info.usteps, 4) if info.halves == 2 else None
     return info, ta, tb, xs
 
 
-@pytest.mark.parametrize("rate,work,l,m", [(48000, 12480, 13, 50), (48000, 16640, 26, 75)])
+@pytest.mark.parametrize("rate,work,l,m", [(48000, 12480, 13, 50), (48000, 16640, 26, 75), (96000, 12480, 13, 100),
+                                           (48000, 20800, 13, 30), (96000, 16640, 13, 75)])
 def test_tile_plan_geometry_reproduces_fast_resampling(na, rate, work, l, m):
     """The tiled kernel's host-built geometry (groups, window starts, the two half windows, zero-padded tap
     records), emulated with numpy, must give fast_resampling's outputs (dsp.rs:186-289) -- vs the oracle."""
     import math
     import oracle
-    f = na.filters.LowpassDcRemoval(na.Freq.hz(4800, rate), 30.0, na.Freq.hz(1000, rate))
+    prof = {12480: "standard", 16640: "fast", 20800: "slow"}[work]
+    st = na.Settings.profile(prof)
+    f = na.filters.LowpassDcRemoval(na.Freq.hz(st.resample_cutout, rate), st.resample_atten,
+                                    na.Freq.hz(st.resample_delta_freq, rate))
     f.resample(rate, rate * l)
     h = f.design()
     info, ta, tb, xs = _tile_plan(na, l, m, h)
     assert info is not None and info.usable
-    assert info.p_out * m == info.p_in * l and info.p_in % 4 == 0 and info.p_out == 8 * info.groups
-    assert (info.slice_stride // 4) % 8 == 2                                       # tap bank-group skew
-    starts = {((r >> 1) * (info.pair_pitch // 4) + (r & 1) * (info.p_in // 4)) % 8 for r in range(8)}
-    assert len(starts) == 8 and info.pair_pitch >= info.p_in + info.row_len        # 8 row lanes, 8 bank groups
+    R = 4 * info.halves
+    assert info.p_out * m == info.p_in * l and info.p_in % 4 == 0 and info.p_out == R * info.groups
+    assert len({(ks * (info.slice_stride // 4)) % 8 for ks in range(4)}) == 4       # tap bank-group skew
+    if info.rows_per_copy == 2:
+        starts = {((r >> 1) * (info.pair_pitch // 4) + (r & 1) * (info.p_in // 4)) % 8 for r in range(8)}
+        assert info.pair_pitch >= info.p_in + info.row_len
+    else:
+        starts = {(r * (info.pair_pitch // 4)) % 8 for r in range(8)}
+        assert info.pair_pitch >= info.row_len
+    assert len(starts) == 8                                                        # 8 row lanes, 8 bank groups
     assert info.usteps == info.half_taps + info.shift == 16 * info.iters and info.shift % 16 == 0
+    assert info.halves == 2 or info.shift == 0
     assert all(int(v) % 4 == 0 and int(v) + info.usteps <= info.row_len for v in xs)
     assert info.ctas_per_sm == 1 and info.smem_bytes <= 227 * 1024
     # the loop skips half B before `shift` and half A after `half_taps`: those taps must be zero
-    assert not tb[:, : info.shift].any() and not ta[:, info.half_taps:].any()
+    assert not ta[:, info.half_taps:].any() and (tb is None or not tb[:, : info.shift].any())
     x = (np.random.default_rng(0).standard_normal(30000) * 1000).astype(np.float32)
     ref = oracle.fast_resampling(x, l, m, h)
     qt, tile_out = info.rows_per_tile, info.rows_per_tile * info.p_out
@@ -191,9 +203,10 @@ def test_tile_plan_geometry_reproduces_fast_resampling(na, rate, work, l, m):
         for q in range(qt):
             for g in range(info.groups):
                 win = xpad[xb + q * info.p_in + int(xs[g]): xb + q * info.p_in + int(xs[g]) + info.usteps]
-                k = t * tile_out + q * info.p_out + 8 * g
+                k = t * tile_out + q * info.p_out + R * g
                 out[k:k + 4] = win @ ta[g].astype(np.float64)
-                out[k + 4:k + 8] = win @ tb[g].astype(np.float64)
+                if tb is not None:
+                    out[k + 4:k + 8] = win @ tb[g].astype(np.float64)
     assert np.max(np.abs(out[:ref.size] - ref)) <= 1e-6 * np.max(np.abs(ref))
 
 
