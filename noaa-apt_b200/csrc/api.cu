@@ -81,9 +81,9 @@ int alloc_sync_buffers(apt_decoder *d) {
     APT_CUDA(cudaMalloc(&d->d_root_list, static_cast<size_t>(d->max_blocks) * p.dist * sizeof(u32)));
     APT_CUDA(cudaMalloc(&d->d_root_count, static_cast<size_t>(d->max_blocks) * sizeof(u32)));
     APT_CUDA(cudaMalloc(&d->d_pos, static_cast<size_t>(d->max_positions) * sizeof(u32)));
-    // parallel picker: room for every row-aligned start plus ~16 roots per row (typical recordings have
-    // ~8); beyond that the kernel falls back to the sequential walk by itself.
-    const u32 cap = static_cast<u32>(std::min<uint64_t>(static_cast<uint64_t>(d->max_positions) * 17 + 65536, 1u << 28));
+    // parallel picker: room for every row-aligned start plus ~63 roots per row (noisy recordings have ~35);
+    // beyond that the kernel falls back to the sequential walk by itself.
+    const u32 cap = static_cast<u32>(std::min<uint64_t>(static_cast<uint64_t>(d->max_positions) * 64 + 65536, 1u << 28));
     APT_CUDA(cudaMalloc(&d->d_pick, pick_scratch_bytes(d->max_blocks, d->max_positions, cap)));
     d->pick = pick_scratch_carve(d->d_pick, d->max_blocks, d->max_positions, cap);
     APT_CUDA(cudaMemset(d->pick.ticket, 0, 8));
