@@ -160,7 +160,13 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
     }
     __syncthreads();
 
-    if (warp == G + E) {
+    // Warp roles.  Warps are spread over the 4 SM sub-partitions round-robin (warp % 4); with 13 compute warps
+    // sub-partition 0 gets four of them and the others three, so the producer (light) goes to sub-partition 0 and
+    // the epilogue warps to the other three.
+    const u32 prod_warp = (G + 3) / 4 * 4;                 // first warp index >= G on sub-partition 0
+    const bool is_producer = warp == prod_warp;
+    const bool is_compute = warp < G;
+    if (is_producer) {
         // ======================================= producer =======================================
         const bool aligned16 = (reinterpret_cast<uintptr_t>(signal) & 15) == 0;
         const u32 w0_last = group_xs[G - 1];
@@ -253,7 +259,7 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
             PROF_ADD(1);
         }
         if (profiling) { prof[0] = pt[0]; prof[1] = pt[1]; }
-    } else if (warp < G) {
+    } else if (is_compute) {
         // ======================================= compute ========================================
         const u32 ks = lane >> 3, ql = lane & 7;
         const u32 w0 = group_xs[warp];
@@ -351,7 +357,7 @@ k_polyphase_ws(const float *__restrict__ signal, u64 len, const float *__restric
         if (profiling && warp == 0) { prof[2] = pt[0]; prof[3] = pt[1]; prof[4] = pt[2]; prof[5] = pt[3]; }
     } else {
         // ======================================= epilogue =======================================
-        const u32 e = warp - G;
+        const u32 e = warp - G - (warp > prod_warp ? 1 : 0);   // epilogue warps: every remaining warp, in order
         const u32 vec_per_row = tp.p_out / 4;
         const u32 nvec = QT * vec_per_row;
         const u32 plane_floats = QT * tp.plane_pitch;

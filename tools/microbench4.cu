@@ -94,6 +94,31 @@ __global__ void __launch_bounds__(1024, 1) k_inner(float *out, long long *cyc, i
                     if (it > 0) half_fma2(ab, tap_addr + 64, s);
                     row_addr += 64; tap_addr += 128;
                 }
+            } else if (VARIANT == 3) {   // ping-pong sample buffers, next iteration's samples requested first
+                float4 s0[4], s1[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s0[j] = lds128(row_addr + j * row_step8);
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) {
+                    row_addr += 64;
+                    if (it + 1 < ITERS) {
+                        if (it & 1) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) s0[j] = lds128(row_addr + j * row_step8);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) s1[j] = lds128(row_addr + j * row_step8);
+                        }
+                    }
+                    if (it & 1) {
+                        if (it < ITERS - 1) half_fma2(aa, tap_addr, s1);
+                        if (it > 0) half_fma2(ab, tap_addr + 64, s1);
+                    } else {
+                        if (it < ITERS - 1) half_fma2(aa, tap_addr, s0);
+                        if (it > 0) half_fma2(ab, tap_addr + 64, s0);
+                    }
+                    tap_addr += 128;
+                }
             } else {   // VARIANT 2: samples of the next iteration are loaded before this iteration's FMAs
                 float4 s[4], sn[4];
 #pragma unroll
@@ -147,5 +172,6 @@ int main() {
     run<0>("FFMA2", 16); run<1>("scalar FFMA", 16); run<2>("FFMA2 + prefetch", 16);
     run<0>("FFMA2", 26); run<1>("scalar FFMA", 26); run<2>("FFMA2 + prefetch", 26);
     run<0>("FFMA2", 8); run<1>("scalar FFMA", 8);
+    run<3>("FFMA2 ping-pong prefetch", 13); run<3>("FFMA2 ping-pong prefetch", 16); run<3>("FFMA2 ping-pong prefetch", 26);
     return 0;
 }
