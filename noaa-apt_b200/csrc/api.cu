@@ -239,7 +239,12 @@ extern "C" int apt_resample_with_filter(const float *signal, uint64_t n, uint32_
         TilePlan tp{};
         std::vector<float> tt;
         std::vector<u32> xs;
-        if (!getenv("APTB200_GENERIC_RESAMPLER") && make_tile_plan(rp.r.l, rp.r.m, rp.taps, tp, tt, xs)) {
+        UtPlan up{};
+        std::vector<float> us;
+        if (!getenv("APTB200_GENERIC_RESAMPLER") && make_ut_plan(rp.r.l, rp.r.m, rp.taps, up, us)) {
+            APT_TRY(launch_polyphase_ut(c, dx.as<float>(), n, dh.as<float>(), up, us, rp.nout, 0, 0, false, 0.f, 1.f, dy.as<float>()));
+            APT_CUDA(cudaDeviceSynchronize());
+        } else if (!getenv("APTB200_GENERIC_RESAMPLER") && make_tile_plan(rp.r.l, rp.r.m, rp.taps, tp, tt, xs)) {
             DevBuf dt, dg;
             APT_TRY(dt.alloc(tt.size() * sizeof(float)));
             APT_TRY(dg.alloc(xs.size() * sizeof(u32)));

@@ -54,6 +54,8 @@ int make_plan(uint32_t input_rate, const apt_settings &s, Plan &p) {
     p.off2 = 2 * ((static_cast<uint64_t>(p.h.size()) - 1) / 2);
     p.tiled = p.first_polyphase && !getenv("APTB200_GENERIC_RESAMPLER") &&
               make_tile_plan(p.first.l, p.first.m, p.h, p.tile, p.tile_taps, p.tile_xs);
+    p.ut = p.first_polyphase && !getenv("APTB200_GENERIC_RESAMPLER") &&
+           make_ut_plan(p.first.l, p.first.m, p.h, p.utp, p.ut_stream);
 
     // decode.rs:95-100
     const float cut = static_cast<float>(kFinalRate) / static_cast<float>(s.work_rate);
@@ -143,6 +145,9 @@ int run_find_sync(apt_decoder *d, uint64_t nwork) {
     return APT_OK;
 }
 
+// one of the two TMA-staged resamplers serves this decoder's first stage
+static bool fast_front(const apt_decoder *d) { return d->plan.ut || (d->plan.tiled && d->d_tile_taps); }
+
 // fast_resampling + demodulate of outputs produced from a device-resident (or staged) chunk.
 // `in` is the address sample 0 of the recording would have (a biased pointer for chunk buffers).
 static int launch_front_polyphase(apt_decoder *d, const void *in, int format, uint64_t n, uint64_t nwork,
@@ -150,6 +155,12 @@ static int launch_front_polyphase(apt_decoder *d, const void *in, int format, ui
                                   float *conv_base /* f32 view of a PCM16 chunk (already biased) or nullptr */) {
     const Plan &p = d->plan;
     const LaunchCtx c{d->stream, d->sm_count};
+    if (p.ut && (format == APT_F32 || conv_base)) {
+        const float *fin = format == APT_F32 ? static_cast<const float *>(in) : conv_base;
+        if ((reinterpret_cast<uintptr_t>(fin) & 15) == 0)
+            return launch_polyphase_ut(c, fin, n, d->d_h, p.utp, p.ut_stream, nwork, tile_begin, tile_end, true, p.cosphi2,
+                                       p.sinphi, d->d_e);
+    }
     if (p.tiled && d->d_tile_taps && (format == APT_F32 || conv_base)) {
         const float *fin = format == APT_F32 ? static_cast<const float *>(in) : conv_base;
         return launch_polyphase_tiled(c, fin, n, d->d_tile_taps, d->d_tile_xs, p.tile, nwork, tile_begin, tile_end, true,
@@ -166,14 +177,27 @@ static int enqueue_front_chunked(apt_decoder *d, const void *host, int format, u
     const LaunchCtx c{d->stream, d->sm_count};
     const size_t sb = format == APT_PCM16 ? 2 : 4;
     const uint64_t cap = d->chunk_samples;
-    const bool tiled = p.tiled && d->d_tile_taps;
+    const bool tiled = fast_front(d);
     const uint64_t l = p.first.l, m = p.first.m;
-    uint64_t units, per_chunk;            // tiles or outputs
-    const uint64_t tile_in = static_cast<uint64_t>(p.tile.qt) * p.tile.p_in, tile_out = static_cast<uint64_t>(p.tile.qt) * p.tile.p_out;
+    uint64_t units, per_chunk;            // tiles / blocks or outputs
+    // a unit (tile of the warp-specialised kernel, block of the uniform-tap kernel) reads unit_in new samples,
+    // plus `before` samples in front of the first unit of a chunk and `after` beyond the start of the last one
+    uint64_t unit_in = 0, unit_out = 0, before = 0, after = 0;
+    if (p.ut) {
+        unit_in = static_cast<uint64_t>(p.utp.rb) * m;
+        unit_out = static_cast<uint64_t>(p.utp.rb) * l;
+        before = p.utp.back;
+        after = p.utp.slot_floats - p.utp.back;           // a block's span beyond its first row's first sample
+    } else if (tiled) {
+        unit_in = static_cast<uint64_t>(p.tile.qt) * p.tile.p_in;
+        unit_out = static_cast<uint64_t>(p.tile.qt) * p.tile.p_out;
+        before = p.tile.p_in - d->plan.tile_xs.back();    // halo row: window of the last group one super-period back
+        after = static_cast<uint64_t>(p.tile.qt - 1) * p.tile.p_in + p.tile.row_len;
+    }
     if (tiled) {
-        units = (nwork + tile_out - 1) / tile_out;
-        if (cap < tile_in + p.tile.row_len + p.tile.p_in + 64) return fail(APT_ERR_BAD_ARG, "chunk too small for one tile");
-        per_chunk = (cap - p.tile.row_len - p.tile.p_in - 64) / tile_in;
+        units = (nwork + unit_out - 1) / unit_out;
+        if (cap < before + after + unit_in + 64) return fail(APT_ERR_BAD_ARG, "chunk too small for one tile");
+        per_chunk = (cap - before - after - 64) / unit_in + 1;
     } else {
         units = nwork;
         const uint64_t halo = p.off2 / l + 4;
@@ -188,9 +212,8 @@ static int enqueue_front_chunked(apt_decoder *d, const void *host, int format, u
         const int b = static_cast<int>(chunk & 1);
         uint64_t xa, xb;
         if (tiled) {
-            // first sample: the halo row of the chunk's first tile (window of the last group one super-period back)
-            xa = u0 == 0 ? 0 : u0 * tile_in - p.tile.p_in + d->plan.tile_xs.back();
-            xb = std::min<uint64_t>(n, (u1 * p.tile.qt - 1) * p.tile.p_in + p.tile.row_len);
+            xa = u0 == 0 ? 0 : u0 * unit_in - before;
+            xb = std::min<uint64_t>(n, (u1 - 1) * unit_in + after);
         } else {
             const uint64_t kfirst = u0 == 0 ? 0 : u0 - 1;                    // the envelope needs r[k0 - 1]
             xa = (kfirst * m + l - 1) / l;
@@ -239,7 +262,7 @@ static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n,
             APT_TRY(enqueue_front_chunked(d, host_chunked, format, n, nwork));
         } else {
             float *conv = nullptr;
-            if (format == APT_PCM16 && p.tiled && d->d_tile_taps && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+            if (format == APT_PCM16 && fast_front(d) && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
                 // the WAV's int16 samples: `as f32` (wav.rs:37) on the device, then the same tiled kernel
                 if (d->conv_cap < n) {
                     if (d->d_conv) APT_CUDA(cudaFree(d->d_conv));

@@ -39,6 +39,9 @@ struct Plan {
     TilePlan tile{};
     std::vector<float> tile_taps;
     std::vector<u32> tile_xs;
+    bool ut = false;               // the uniform-tap resampler (taps as a kernel parameter) fits: preferred
+    UtPlan utp{};
+    std::vector<float> ut_stream;
 };
 
 int make_plan(uint32_t input_rate, const apt_settings &s, Plan &plan);

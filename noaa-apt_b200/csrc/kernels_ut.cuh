@@ -1,0 +1,263 @@
+// Polyphase resampler + envelope with the taps in the CONSTANT BANK (kernel parameter), read through the
+// uniform datapath -- the hot kernel of the path for small L (48/96/192 kHz -> 12 480 Hz has L = 13).
+// fast_resampling dsp.rs:186-289 + demodulate dsp.rs:350-383.
+//
+// Formulation.  Output k = L*q + r ("row" q, phase r < L) is
+//     y[L*q + r] = sum_u h[u*L - r*M] * X[q*M + u]
+// i.e. every row uses the SAME L tap sets T[u][r] = h[u*L - r*M] on a window that moves by M samples per row.
+// A thread owns Q rows x all L outputs of each (NP = ceil(L/2) packed fp32x2 accumulators per row); the 32 lanes
+// of a warp are 32 consecutive rows.  The tap pair (T[u][2p], T[u][2p+1]) is therefore warp-uniform: it is read
+// with LDCU from the kernel-parameter constant bank into uniform registers and used directly as the packed
+// operand of FFMA2 (`FFMA2 R, R.F32, UR.F32x2, R`); the only shared-memory traffic is the thread's own samples
+// (one 4-sample chunk per row per 4*NP FFMA2).  Measured (profiles/r01_microbench_uniform_taps.txt): 104-107
+// FMA/clk/SM, the FFMA2 pipe limit, against 70-84 for shared-memory tap operands.
+//
+// Zero padding.  Pair p only sees samples fx(2p) .. lx(2p+1); the loop over 4-sample chunks is cut into
+// segments with a fixed set of active pairs: ramp-up (pairs 0..a-1 for a = 1..NP-1), steady (all), ramp-down
+// (pairs a..NP-1).  The tap stream in the parameter block is stored in exactly the order the loop consumes it.
+//
+// Pipeline.  One persistent CTA per SM owns a contiguous range of blocks (block = 32*Q rows = 32*Q*L outputs,
+// whose input is ONE contiguous span of the signal: no duplication in shared memory).  A producer warp streams
+// blocks into a ring of NSLOT shared-memory slots with one cp.async.bulk (TMA) per block, completion on a
+// full mbarrier; W compute warps take blocks off the ring in order (shared-memory ticket), compute, turn
+// (r[k-1], r[k]) into the envelope, transpose the block's outputs through the (now dead) slot and store
+// coalesced float4; an empty mbarrier hands the slot back.  Warps are not coupled by any CTA-wide barrier.
+// r[k0-1] for the first output of a block is a k-split dot product over the warp (taps from global memory).
+#pragma once
+
+
+#include <cstdint>
+#include <utility>
+#include <cuda_runtime.h>
+
+#include "kernels_fast.cuh"
+#include "launch.hpp"
+
+namespace aptb200 {
+
+constexpr int kUtMaxPairs = 8;
+
+// Kernel-parameter block: everything in it is warp-uniform.  MAXV float4 = the tap stream.
+template <int MAXV>
+struct UtParams {
+    float4 v[MAXV];
+    u32 cs[kUtMaxPairs];      // first chunk of pair p
+    u32 ce[kUtMaxPairs];      // one past its last chunk
+};
+
+struct UtGeom {
+    u32 l, m;
+    u32 back;                 // samples staged in front of the block's first row (halo window), multiple of 4
+    u32 slot_floats;          // back + (rows-1)*m + 4*chunks, multiple of 4
+    u32 nslot, warps;         // ring slots, compute warps
+    u32 halo_u0, halo_n;      // output L-1: first sample (relative to its row) and number of taps
+    u32 debug;
+};
+
+template <int VEC>
+__device__ __forceinline__ void ut_load4(const float *p, float (&s)[4]) {
+    if (VEC == 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(p);
+        s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+    } else if (VEC == 2) {
+        const float2 a = *reinterpret_cast<const float2 *>(p), b = *reinterpret_cast<const float2 *>(p + 2);
+        s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y;
+    } else {
+        s[0] = p[0]; s[1] = p[1]; s[2] = p[2]; s[3] = p[3];
+    }
+}
+
+// Chunks [cb, ce) with pairs [P0, P1) active.  toff: running float4 index into the tap stream (uniform).
+template <int P0, int P1, int NP, int Q, int VEC, int MAXV>
+__device__ __forceinline__ void ut_segment(const UtParams<MAXV> &prm, u32 cb, u32 ce, u32 &toff,
+                                           const float *row0, u32 qstride, f32x2 (&acc)[Q][NP]) {
+#pragma unroll 1
+    for (u32 c = cb; c < ce; ++c) {
+        float s[Q][4];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) ut_load4<VEC>(row0 + q * qstride + 4 * c, s[q]);
+#pragma unroll
+        for (int p = P0; p < P1; ++p) {
+            const float4 ta = prm.v[toff + 2 * (p - P0)], tb = prm.v[toff + 2 * (p - P0) + 1];
+            const f32x2 t0 = pack2(ta.x, ta.y), t1 = pack2(ta.z, ta.w), t2 = pack2(tb.x, tb.y), t3 = pack2(tb.z, tb.w);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                acc[q][p] = fma2(t0, pack2(s[q][0], s[q][0]), acc[q][p]);
+                acc[q][p] = fma2(t1, pack2(s[q][1], s[q][1]), acc[q][p]);
+                acc[q][p] = fma2(t2, pack2(s[q][2], s[q][2]), acc[q][p]);
+                acc[q][p] = fma2(t3, pack2(s[q][3], s[q][3]), acc[q][p]);
+            }
+        }
+        toff += 2 * (P1 - P0);
+    }
+}
+
+template <int NP, int Q, int VEC, int MAXV, int... A>
+__device__ __forceinline__ void ut_ramp_up(const UtParams<MAXV> &prm, u32 &toff, const float *row0, u32 qstride,
+                                           f32x2 (&acc)[Q][NP], std::integer_sequence<int, A...>) {
+    (ut_segment<0, A + 1, NP, Q, VEC, MAXV>(prm, prm.cs[A], prm.cs[A + 1], toff, row0, qstride, acc), ...);
+}
+template <int NP, int Q, int VEC, int MAXV, int... A>
+__device__ __forceinline__ void ut_ramp_down(const UtParams<MAXV> &prm, u32 &toff, const float *row0, u32 qstride,
+                                             f32x2 (&acc)[Q][NP], std::integer_sequence<int, A...>) {
+    (ut_segment<A + 1, NP, NP, Q, VEC, MAXV>(prm, prm.ce[A], prm.ce[A + 1], toff, row0, qstride, acc), ...);
+}
+
+template <int L, int Q, int VEC, int MAXV, bool ENVELOPE>
+__global__ void __launch_bounds__(512, 1)
+k_polyphase_ut(const __grid_constant__ UtParams<MAXV> prm, const float *__restrict__ signal, u64 len,
+               const float *__restrict__ h, const UtGeom g, u64 nout, u64 blk_begin, u64 blk_end, float cosphi2,
+               float inv_sinphi, float *__restrict__ out) {
+    extern __shared__ __align__(128) unsigned char ut_smem[];
+    u64 *full = reinterpret_cast<u64 *>(ut_smem);                 // [kUtMaxSlots]
+    u64 *empty = full + kUtMaxSlots;                               // [kUtMaxSlots]
+    u32 *ticket = reinterpret_cast<u32 *>(empty + kUtMaxSlots);    // next block sequence number
+    float *slots = reinterpret_cast<float *>(ut_smem + 512);
+
+    constexpr u32 RB = 32 * Q;                                     // rows per block
+    constexpr int NP = (L + 1) / 2;                                // packed accumulators per row
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr u32 l = L;
+    const u32 m = g.m;
+    // this CTA's contiguous range of blocks
+    const u64 nb_all = blk_end - blk_begin;
+    const u64 b0 = blk_begin + nb_all * blockIdx.x / gridDim.x;
+    const u64 b1 = blk_begin + nb_all * (blockIdx.x + 1) / gridDim.x;
+    const u32 nblk = static_cast<u32>(b1 - b0);
+
+    if (threadIdx.x == 0) {
+        for (u32 s = 0; s < g.nslot; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        *ticket = 0;
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == g.warps) {
+        // ===== producer warp =====
+        for (u32 n = 0; n < nblk; ++n) {
+            const u32 s = n % g.nslot;
+            if (n >= g.nslot) mbar_wait(empty + s, ((n / g.nslot) - 1) & 1);
+            float *dst = slots + static_cast<size_t>(s) * g.slot_floats;
+            const long long x_lo = static_cast<long long>((b0 + n) * RB * m) - g.back;   // sample staged at dst[0]
+            const long long x_hi = x_lo + g.slot_floats;
+            if (x_lo >= 0 && static_cast<u64>(x_hi) <= len) {
+                if (lane == 0) {
+                    mbar_expect_tx(full + s, g.slot_floats * 4);
+                    tma_bulk_g2s(dst, signal + x_lo, g.slot_floats * 4, full + s);
+                }
+            } else {
+                // first / last blocks: bulk-copy the part that exists (16-byte granules), fill the rest
+                const long long va = x_lo < 0 ? 0 : x_lo;                                 // x_lo is a multiple of 4
+                long long vb = static_cast<long long>(len) < x_hi ? static_cast<long long>(len) : x_hi;
+                if (vb < va) vb = va;
+                const long long vb4 = va + ((vb - va) & ~3ll);
+                for (long long x = x_lo + lane; x < x_hi; x += 32)
+                    if (x < va || x >= vb4) dst[x - x_lo] = (x >= va && x < vb) ? __ldg(signal + x) : 0.f;
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    const u32 bytes = static_cast<u32>(vb4 - va) * 4;
+                    if (bytes) {
+                        mbar_expect_tx(full + s, bytes);
+                        tma_bulk_g2s(dst + (va - x_lo), signal + va, bytes, full + s);
+                    } else {
+                        mbar_arrive(full + s);
+                    }
+                }
+            }
+        }
+        return;
+    }
+    if (warp > g.warps) return;
+
+    // ===== compute warps =====
+    const u32 qstride = 32 * m;
+    for (;;) {
+        u32 n = 0;
+        if (lane == 0) n = atomicAdd(ticket, 1u);
+        n = __shfl_sync(0xffffffffu, n, 0);
+        if (n >= nblk) break;
+        const u32 s = n % g.nslot;
+        float *slot = slots + static_cast<size_t>(s) * g.slot_floats;
+        mbar_wait(full + s, (n / g.nslot) & 1);
+        const u64 blk = b0 + n;
+        const u64 k0 = blk * RB * l;                               // first output of the block
+
+        f32x2 acc[Q][NP];
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+#pragma unroll
+            for (int p = 0; p < NP; ++p) acc[q][p] = 0ull;
+        const float *row0 = slot + g.back + lane * m;
+        u32 toff = 0;
+        if (g.debug != 1) {
+            ut_ramp_up<NP, Q, VEC, MAXV>(prm, toff, row0, qstride, acc, std::make_integer_sequence<int, NP - 1>{});
+            ut_segment<0, NP, NP, Q, VEC, MAXV>(prm, prm.cs[NP - 1], prm.ce[0], toff, row0, qstride, acc);
+            ut_ramp_down<NP, Q, VEC, MAXV>(prm, toff, row0, qstride, acc, std::make_integer_sequence<int, NP - 1>{});
+        }
+
+        // r[k0 - 1]: output L-1 of the row in front of the block, k-split over the lanes
+        float halo = 0.f;
+        if (ENVELOPE && k0 > 0) {
+            const float *hw = slot + g.back - m;                   // that row's sample u sits at hw[u]
+            for (u32 i = lane; i < g.halo_n; i += 32) {
+                const u32 u = g.halo_u0 + i;
+                halo = fmaf(__ldg(h + (u * l - (l - 1) * m)), hw[u], halo);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) halo += __shfl_xor_sync(0xffffffffu, halo, o);
+        }
+
+        // ---- epilogue: envelope, transpose through the slot, coalesced stores ----
+        __syncwarp();                                              // every lane is done reading the samples
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            float r[2 * NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) unpack2(acc[q][p], r[2 * p], r[2 * p + 1]);
+            float *dst = slot + (q * 32 + lane) * l;
+            if (ENVELOPE) {
+                // the output in front of this row's first: last output of the previous row (lane - 1, or the
+                // previous set of 32 rows' lane 31, or the halo)
+                const float last = r[L - 1];
+                // exchanged through the slot (behind the staged outputs), not with SHFL: warp shuffles in this
+                // loop body make the compiler keep the tap-stream offset in a vector register (LDC instead of LDCU)
+                float *xch = slot + RB * l;
+                xch[q * 32 + lane] = last;
+                __syncwarp();
+                float prev = (q * 32 + lane) == 0 ? halo : xch[q * 32 + lane - 1];
+#pragma unroll
+                for (int j = 0; j < L; ++j) {
+                    dst[j] = envelope2_fast(prev, r[j], cosphi2, inv_sinphi);
+                    prev = r[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < L; ++j) dst[j] = r[j];
+            }
+        }
+        __syncwarp();
+        const u32 nvec = RB * l / 4;                               // RB*l is a multiple of 4
+        for (u32 v = lane; v < nvec; v += 32) {
+            const u64 k = k0 + 4 * v;
+            if (k >= nout) break;
+            float4 val = *reinterpret_cast<const float4 *>(slot + 4 * v);
+            if (ENVELOPE && k == 0) val.x = 0.f;                   // dsp.rs:364: the first sample has no predecessor
+            if (k + 3 < nout) {
+                *reinterpret_cast<float4 *>(out + k) = val;
+            } else {
+                out[k] = val.x;
+                if (k + 1 < nout) out[k + 1] = val.y;
+                if (k + 2 < nout) out[k + 2] = val.z;
+            }
+        }
+        fence_proxy_async();                                       // generic writes before the next bulk copy into the slot
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+}
+
+}  // namespace aptb200

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "aptb200.h"
 #include "common.hpp"
@@ -11,6 +12,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_lpsync.cuh"
 #include "kernels_sync.cuh"
+#include "kernels_ut.cuh"
 
 namespace aptb200 {
 
@@ -95,6 +97,62 @@ int launch_polyphase_tiled(const LaunchCtx &c, const float *signal, u64 len, con
         fprintf(stderr, "\n");
     }
     return APT_OK;
+}
+
+namespace {
+template <int Q, int VEC, int MAXV, bool ENV>
+int launch_ut_inst(const LaunchCtx &c, const float *signal, u64 len, const float *h, const UtPlan &up,
+                   const std::vector<float> &stream, u64 nout, u64 blk_begin, u64 blk_end, float cosphi2, float sinphi,
+                   float *out) {
+    static thread_local UtParams<MAXV> prm;                      // 6 / 30 KB: rebuilt per launch, passed by value
+    memset(&prm, 0, sizeof(prm));
+    memcpy(prm.v, stream.data(), stream.size() * sizeof(float));
+    for (int p = 0; p < 8; ++p) {
+        prm.cs[p] = up.cs[p];
+        prm.ce[p] = up.ce[p];
+    }
+    const UtGeom g{up.l, up.m, up.back, up.slot_floats, up.nslot, up.warps, up.halo_u0, up.halo_n, up.debug};
+    auto kern = k_polyphase_ut<static_cast<int>(kUtL), Q, VEC, MAXV, ENV>;
+    APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(up.smem_bytes)));
+    const unsigned grid = static_cast<unsigned>(std::min<u64>(blk_end - blk_begin, static_cast<u64>(c.sm_count)));
+    kern<<<grid, 32 * (up.warps + 1), up.smem_bytes, c.stream>>>(prm, signal, len, h, g, nout, blk_begin, blk_end, cosphi2,
+                                                                 1.0f / sinphi, out);
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+template <int Q, int VEC, bool ENV>
+int launch_ut_size(const LaunchCtx &c, const float *signal, u64 len, const float *h, const UtPlan &up,
+                   const std::vector<float> &stream, u64 nout, u64 b0, u64 b1, float cosphi2, float sinphi, float *out) {
+    if (up.nvec <= kUtMaxVecSmall)
+        return launch_ut_inst<Q, VEC, static_cast<int>(kUtMaxVecSmall), ENV>(c, signal, len, h, up, stream, nout, b0, b1, cosphi2, sinphi, out);
+    return launch_ut_inst<Q, VEC, static_cast<int>(kUtMaxVecLarge), ENV>(c, signal, len, h, up, stream, nout, b0, b1, cosphi2, sinphi, out);
+}
+template <int Q, bool ENV>
+int launch_ut_vec(const LaunchCtx &c, const float *signal, u64 len, const float *h, const UtPlan &up,
+                  const std::vector<float> &stream, u64 nout, u64 b0, u64 b1, float cosphi2, float sinphi, float *out) {
+    switch (up.vec) {
+    case 4: return launch_ut_size<Q, 4, ENV>(c, signal, len, h, up, stream, nout, b0, b1, cosphi2, sinphi, out);
+    case 2: return launch_ut_size<Q, 2, ENV>(c, signal, len, h, up, stream, nout, b0, b1, cosphi2, sinphi, out);
+    default: return launch_ut_size<Q, 1, ENV>(c, signal, len, h, up, stream, nout, b0, b1, cosphi2, sinphi, out);
+    }
+}
+}  // namespace
+
+int launch_polyphase_ut(const LaunchCtx &c, const float *signal, u64 len, const float *h, const UtPlan &up,
+                        const std::vector<float> &stream, u64 nout, u64 blk_begin, u64 blk_end, bool envelope,
+                        float cosphi2, float sinphi, float *out) {
+    if (nout == 0) return APT_OK;
+    const u64 blk_out = static_cast<u64>(up.rb) * up.l;
+    u64 nblk = (nout + blk_out - 1) / blk_out;
+    if (blk_end != 0) nblk = std::min(nblk, blk_end);
+    if (blk_begin >= nblk) return APT_OK;
+    if ((reinterpret_cast<uintptr_t>(signal) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || stream.size() != 4ull * up.nvec)
+        return fail(APT_ERR_BAD_ARG, "uniform-tap resampler: misaligned buffers or inconsistent plan");
+    if (up.q == 2)
+        return envelope ? launch_ut_vec<2, true>(c, signal, len, h, up, stream, nout, blk_begin, nblk, cosphi2, sinphi, out)
+                        : launch_ut_vec<2, false>(c, signal, len, h, up, stream, nout, blk_begin, nblk, cosphi2, sinphi, out);
+    return envelope ? launch_ut_vec<1, true>(c, signal, len, h, up, stream, nout, blk_begin, nblk, cosphi2, sinphi, out)
+                    : launch_ut_vec<1, false>(c, signal, len, h, up, stream, nout, blk_begin, nblk, cosphi2, sinphi, out);
 }
 
 int launch_fir_decimate(const LaunchCtx &c, const void *signal, int format, const float *coeff, u32 ntaps, u32 m,

@@ -60,6 +60,30 @@ struct TilePlan {
     u32 debug;         // 0 normal; 1 skip the FMA loop; 2 skip the loads (timing experiments only)
 };
 
+// Geometry of the uniform-tap kernel (kernels_ut.cuh) for one (L, M, taps) triple; built by make_ut_plan.
+constexpr u32 kUtL = 13;               // the interpolation factor the kernel is instantiated for (48/96/192 kHz -> 12 480 Hz)
+constexpr u32 kUtPairs = (kUtL + 1) / 2;   // packed accumulators per row
+constexpr u32 kUtMaxVecSmall = 384;    // float4 entries of the tap stream: small / large parameter block
+constexpr u32 kUtMaxVecLarge = 1900;
+constexpr u32 kUtMaxSlots = 24;
+struct UtPlan {
+    u32 l, m;
+    u32 np;            // pairs of outputs per row = ceil(L/2)
+    u32 q;             // rows per thread (2, or 1 when the rows are long: 96 kHz input)
+    u32 rb;            // rows per block = 32*q; a block = rb*L outputs from one contiguous span of the signal
+    u32 vec;           // 4/2/1: widest aligned shared-memory load of a row's samples (M % 4 == 0 / M % 2 == 0 / odd)
+    u32 back;          // samples staged in front of a block's first row (window of output k0-1), multiple of 4
+    u32 chunks;        // a row touches samples [0, 4*chunks)
+    u32 slot_floats;   // floats of one ring slot = back + (rb-1)*M + 4*chunks, rounded up to 4
+    u32 nslot, warps;  // ring slots, compute warps
+    u32 smem_bytes;
+    u32 nvec;          // float4 entries of the tap stream
+    u32 halo_u0, halo_n;   // output L-1: first sample relative to its row, number of taps
+    u32 cs[8], ce[8];  // pair p is active in chunks [cs[p], ce[p])
+    u64 off2;
+    u32 debug;
+};
+
 struct LaunchCtx {
     cudaStream_t stream;
     int sm_count;
@@ -107,5 +131,14 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
 int launch_polyphase_tiled(const LaunchCtx &c, const float *signal, u64 len, const float *tile_taps,
                            const u32 *group_xs, const TilePlan &tp, u64 nout, u64 tile_begin, u64 tile_end,
                            bool envelope, float cosphi2, float sinphi, float *out);
+
+// Uniform-tap resampler (+ envelope): taps travel as a kernel parameter.  Returns false from make_ut_plan when
+// (l, m, taps) does not fit (L other than 13/14, tap stream too long, rows too long for shared memory).
+bool make_ut_plan(u32 l, u32 m, const std::vector<float> &taps, UtPlan &up, std::vector<float> &stream);
+// Blocks [blk_begin, blk_end) (blk_end == 0: all); `signal` is the 16-byte-aligned address sample 0 would have;
+// `h` the filter taps in device memory (for the one halo output per block).
+int launch_polyphase_ut(const LaunchCtx &c, const float *signal, u64 len, const float *h, const UtPlan &up,
+                        const std::vector<float> &stream, u64 nout, u64 blk_begin, u64 blk_end, bool envelope,
+                        float cosphi2, float sinphi, float *out);
 
 }  // namespace aptb200
