@@ -50,6 +50,12 @@ class CTileInfo(C.Structure):
                                           "group_stride", "ctas_per_sm", "pair_pitch", "halves", "rows_per_copy")]
 
 
+class CUtInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("usable", "l", "m", "np", "q", "rows_per_block", "vec", "back", "chunks",
+                                          "slot_floats", "slot_stride", "nslot", "warps", "smem_bytes", "nvec",
+                                          "stream_b", "halo_u0", "halo_n")] + [("cs", C.c_uint32 * 8), ("ce", C.c_uint32 * 8)]
+
+
 STATUS_CB = C.CFUNCTYPE(None, C.c_float, C.c_char_p, C.c_void_p)
 
 # name -> (restype, argtypes); every symbol include/aptb200.h declares.
@@ -102,6 +108,7 @@ SIGNATURES = {
     "apt_device_free": (None, [C.c_int, C.c_void_p]),
     "apt_memcpy_h2d": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "apt_memcpy_d2h": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "apt_ut_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(CUtInfo), C.c_void_p, C.c_size_t]),
     "apt_tile_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(CTileInfo), C.c_void_p,
                                 C.c_size_t, C.c_void_p, C.c_size_t]),
     "apt_decode_batch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, _u64p, C.c_int, C.c_uint32, C.POINTER(CSettings),

@@ -749,6 +749,26 @@ extern "C" int apt_tile_plan(uint32_t l, uint32_t m, const float *taps, size_t n
     return APT_OK;
 }
 
+extern "C" int apt_ut_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_ut_info *info, float *stream,
+                           size_t cap_stream) {
+    if (!taps || !info) return fail(APT_ERR_BAD_ARG, "null argument");
+    std::vector<float> h(taps, taps + ntaps), st;
+    UtPlan up{};
+    memset(info, 0, sizeof(*info));
+    if (!make_ut_plan(l, m, h, up, st)) return APT_OK;
+    info->usable = 1;
+    info->l = up.l; info->m = up.m; info->np = up.np; info->q = up.q; info->rows_per_block = up.rb; info->vec = up.vec;
+    info->back = up.back; info->chunks = up.chunks; info->slot_floats = up.slot_floats; info->slot_stride = up.slot_stride;
+    info->nslot = up.nslot; info->warps = up.warps; info->smem_bytes = up.smem_bytes; info->nvec = up.nvec;
+    info->stream_b = up.stream_b; info->halo_u0 = up.halo_u0; info->halo_n = up.halo_n;
+    for (int p = 0; p < 8; ++p) {
+        info->cs[p] = up.cs[p];
+        info->ce[p] = up.ce[p];
+    }
+    if (stream) memcpy(stream, st.data(), std::min(cap_stream, st.size()) * sizeof(float));
+    return APT_OK;
+}
+
 // ===================================================================================== batch
 
 extern "C" int apt_decode_batch(const void *const *signals, int format, const uint64_t *lens, int count,

@@ -51,6 +51,9 @@ struct UtGeom {
     u32 slot_floats;          // back + (rows-1)*m + 4*chunks, multiple of 4
     u32 nslot, warps;         // ring slots, compute warps
     u32 halo_u0, halo_n;      // output L-1: first sample (relative to its row) and number of taps
+    u32 header_bytes;         // barriers + halo taps, multiple of 128
+    u32 slot_stride;          // floats between slots: slot_floats + the 2*rows+4 exchange words behind each slot
+    u32 stream_b;             // float4 index where the second role's tap stream starts
     u32 debug;
 };
 
@@ -67,15 +70,18 @@ __device__ __forceinline__ void ut_load4(const float *p, float (&s)[4]) {
     }
 }
 
-// Chunks [cb, ce) with pairs [P0, P1) active.  toff: running float4 index into the tap stream (uniform).
-template <int P0, int P1, int NP, int Q, int VEC, int MAXV>
-__device__ __forceinline__ void ut_segment(const UtParams<MAXV> &prm, u32 cb, u32 ce, u32 &toff,
-                                           const float *row0, u32 qstride, f32x2 (&acc)[Q][NP]) {
+// Chunks [cb, ce) with pairs [P0, P1) of a role active.  toff: running float4 index into the tap stream (uniform).
+// `s` holds the samples of chunk cb on entry and of chunk ce on exit (software prefetch: the loads of chunk
+// c+1 are issued before the FFMA2s of chunk c; `clast` clamps the prefetch of the row's last chunk).
+template <int P0, int P1, int NPR, int Q, int VEC, int MAXV>
+__device__ __forceinline__ void ut_segment(const UtParams<MAXV> &prm, u32 cb, u32 ce, u32 clast, int &toff,
+                                           const float *row0, u32 qstride, f32x2 (&acc)[Q][NPR], float (&s)[Q][4]) {
 #pragma unroll 1
     for (u32 c = cb; c < ce; ++c) {
-        float s[Q][4];
+        float sn[Q][4];
+        const u32 cn = c + 1 < clast ? c + 1 : clast;
 #pragma unroll
-        for (int q = 0; q < Q; ++q) ut_load4<VEC>(row0 + q * qstride + 4 * c, s[q]);
+        for (int q = 0; q < Q; ++q) ut_load4<VEC>(row0 + q * qstride + 4 * cn, sn[q]);
 #pragma unroll
         for (int p = P0; p < P1; ++p) {
             const float4 ta = prm.v[toff + 2 * (p - P0)], tb = prm.v[toff + 2 * (p - P0) + 1];
@@ -89,35 +95,149 @@ __device__ __forceinline__ void ut_segment(const UtParams<MAXV> &prm, u32 cb, u3
             }
         }
         toff += 2 * (P1 - P0);
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s[q][u] = sn[q][u];
     }
 }
 
-template <int NP, int Q, int VEC, int MAXV, int... A>
-__device__ __forceinline__ void ut_ramp_up(const UtParams<MAXV> &prm, u32 &toff, const float *row0, u32 qstride,
-                                           f32x2 (&acc)[Q][NP], std::integer_sequence<int, A...>) {
-    (ut_segment<0, A + 1, NP, Q, VEC, MAXV>(prm, prm.cs[A], prm.cs[A + 1], toff, row0, qstride, acc), ...);
+// One role = a contiguous range of pairs [PB, PB + NPR) of the row's outputs; its loop over chunks is cut into
+// ramp-up (pairs PB..PB+a-1 active), steady (all) and ramp-down (pairs PB+a.. active) segments.
+template <int PB, int NPR, int Q, int VEC, int MAXV, int... A>
+__device__ __forceinline__ void ut_ramp_up(const UtParams<MAXV> &prm, u32 clast, int &toff, const float *row0, u32 qstride,
+                                           f32x2 (&acc)[Q][NPR], float (&s)[Q][4], std::integer_sequence<int, A...>) {
+    (ut_segment<0, A + 1, NPR, Q, VEC, MAXV>(prm, prm.cs[PB + A], prm.cs[PB + A + 1], clast, toff, row0, qstride, acc, s), ...);
 }
-template <int NP, int Q, int VEC, int MAXV, int... A>
-__device__ __forceinline__ void ut_ramp_down(const UtParams<MAXV> &prm, u32 &toff, const float *row0, u32 qstride,
-                                             f32x2 (&acc)[Q][NP], std::integer_sequence<int, A...>) {
-    (ut_segment<A + 1, NP, NP, Q, VEC, MAXV>(prm, prm.ce[A], prm.ce[A + 1], toff, row0, qstride, acc), ...);
+template <int PB, int NPR, int Q, int VEC, int MAXV, int... A>
+__device__ __forceinline__ void ut_ramp_down(const UtParams<MAXV> &prm, u32 clast, int &toff, const float *row0, u32 qstride,
+                                             f32x2 (&acc)[Q][NPR], float (&s)[Q][4], std::integer_sequence<int, A...>) {
+    (ut_segment<A + 1, NPR, NPR, Q, VEC, MAXV>(prm, prm.ce[PB + A], prm.ce[PB + A + 1], clast, toff, row0, qstride, acc, s), ...);
+}
+
+// Everything one warp does for one (block, role): FMA loop over the role's pairs, exchange of the boundary
+// outputs with the partner warp, envelope, staging, its half of the coalesced stores.
+template <int L, int PB, int NPR, bool LAST, int Q, int VEC, int MAXV, bool ENVELOPE>
+__device__ __forceinline__ void ut_role(const UtParams<MAXV> &prm, const UtGeom &g, int toff, float *slot, u64 *xch_bar,
+                                        u64 *staged_bar, u32 parity, u32 role, const float *halo_taps, u64 k0, u64 nout,
+                                        float cosphi2, float inv_sinphi, float *__restrict__ out, u32 lane, bool profiling,
+                                        unsigned long long *prof, long long &pt) {
+#define UT_MARK(slot_)                                   \
+    if (profiling) {                                     \
+        const long long now_ = clock64();                \
+        prof[slot_] += now_ - pt;                        \
+        pt = now_;                                       \
+    }
+    constexpr u32 RB = 32 * Q;
+    constexpr int JB = 2 * PB;                                       // first output (phase) of this role
+    constexpr int JN = (2 * NPR < L - JB) ? 2 * NPR : L - JB;        // number of real outputs
+    const u32 m = g.m, qstride = 32 * m;
+    f32x2 acc[Q][NPR];
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int p = 0; p < NPR; ++p) acc[q][p] = 0ull;
+    const float *row0 = slot + g.back + lane * m;
+    if (g.debug != 1) {
+        const u32 clast = prm.ce[PB + NPR - 1] - 1;
+        float s[Q][4];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) ut_load4<VEC>(row0 + q * qstride + 4 * prm.cs[PB], s[q]);
+        ut_ramp_up<PB, NPR, Q, VEC, MAXV>(prm, clast, toff, row0, qstride, acc, s, std::make_integer_sequence<int, NPR - 1>{});
+        ut_segment<0, NPR, NPR, Q, VEC, MAXV>(prm, prm.cs[PB + NPR - 1], prm.ce[PB], clast, toff, row0, qstride, acc, s);
+        ut_ramp_down<PB, NPR, Q, VEC, MAXV>(prm, clast, toff, row0, qstride, acc, s, std::make_integer_sequence<int, NPR - 1>{});
+    }
+    UT_MARK(2)
+    // boundary outputs, exchanged through the words behind the slot's samples:
+    //   xa[row]     = output JN-1 of the first role (needed by the second role's first output)
+    //   xb[row + 1] = output L-1 of the row (needed by the next row's output 0); xb[0] = r[k0-1] (halo)
+    float *xa = slot + g.slot_floats, *xb = xa + RB;
+    if (ENVELOPE) {
+        if (LAST) {
+            // r[k0 - 1]: output L-1 of the row in front of the block, k-split over the lanes
+            float halo = 0.f;
+            if (k0 > 0) {
+                const float *hw = slot + g.back - m;                   // that row's sample u sits at hw[u]
+                for (u32 i = lane; i < g.halo_n; i += 32) halo = fmaf(halo_taps[i], hw[g.halo_u0 + i], halo);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) halo += __shfl_xor_sync(0xffffffffu, halo, o);
+            }
+            if (lane == 0) xb[0] = halo;
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            float lo, hi;
+            unpack2(acc[q][(JN - 1) / 2], lo, hi);
+            const float last = (JN - 1) % 2 ? hi : lo;
+            if (LAST) xb[q * 32 + lane + 1] = last;
+            else xa[q * 32 + lane] = last;
+        }
+    }
+    UT_MARK(3)
+    // both warps are past the FMA loop (nobody reads the samples any more) and have published
+    __syncwarp();
+    if (lane == 0) mbar_arrive(xch_bar);
+    mbar_wait(xch_bar, parity);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        float r[2 * NPR];
+#pragma unroll
+        for (int p = 0; p < NPR; ++p) unpack2(acc[q][p], r[2 * p], r[2 * p + 1]);
+        const u32 row = q * 32 + lane;
+        float *dst = slot + row * L + JB;
+        if (ENVELOPE) {
+            float prev = LAST ? xa[row] : xb[row];
+#pragma unroll
+            for (int j = 0; j < JN; ++j) {
+                dst[j] = envelope2_fast(prev, r[j], cosphi2, inv_sinphi);
+                prev = r[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < JN; ++j) dst[j] = r[j];
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(staged_bar);
+    mbar_wait(staged_bar, parity);
+    UT_MARK(4)
+    constexpr u32 nvec = RB * L / 4;                                   // RB*L is a multiple of 4
+#pragma unroll
+    for (u32 vi = 0; vi < (nvec + 63) / 64; ++vi) {
+        const u32 v = lane + 32 * (2 * vi + role);
+        const u64 k = k0 + 4 * v;
+        if (v >= nvec || k >= nout) break;
+        float4 val = *reinterpret_cast<const float4 *>(slot + 4 * v);
+        if (ENVELOPE && k == 0) val.x = 0.f;                           // dsp.rs:364: the first sample has no predecessor
+        if (k + 3 < nout) {
+            *reinterpret_cast<float4 *>(out + k) = val;
+        } else {
+            out[k] = val.x;
+            if (k + 1 < nout) out[k + 1] = val.y;
+            if (k + 2 < nout) out[k + 2] = val.z;
+        }
+    }
+#undef UT_MARK
 }
 
 template <int L, int Q, int VEC, int MAXV, bool ENVELOPE>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(Q >= 4 ? 512 : 800, 1)
 k_polyphase_ut(const __grid_constant__ UtParams<MAXV> prm, const float *__restrict__ signal, u64 len,
                const float *__restrict__ h, const UtGeom g, u64 nout, u64 blk_begin, u64 blk_end, float cosphi2,
-               float inv_sinphi, float *__restrict__ out) {
+               float inv_sinphi, float *__restrict__ out, unsigned long long *__restrict__ prof) {
     extern __shared__ __align__(128) unsigned char ut_smem[];
-    u64 *full = reinterpret_cast<u64 *>(ut_smem);                 // [kUtMaxSlots]
-    u64 *empty = full + kUtMaxSlots;                               // [kUtMaxSlots]
-    u32 *ticket = reinterpret_cast<u32 *>(empty + kUtMaxSlots);    // next block sequence number
-    float *slots = reinterpret_cast<float *>(ut_smem + 512);
+    u64 *full = reinterpret_cast<u64 *>(ut_smem);                 // [kUtMaxSlots] samples landed
+    u64 *empty = full + kUtMaxSlots;                               // slot may be refilled (both warps done)
+    u64 *xch = empty + kUtMaxSlots;                                // both warps past the FMA loop, boundary outputs published
+    u64 *staged = xch + kUtMaxSlots;                               // both warps have staged their outputs
+    u32 *ticket = reinterpret_cast<u32 *>(staged + kUtMaxSlots);   // next (block, role) sequence number
+    float *halo_taps = reinterpret_cast<float *>(ut_smem + 1024);  // [halo_n] taps of output L-1 (for r[k0-1])
+    float *slots = reinterpret_cast<float *>(ut_smem + g.header_bytes);
 
     constexpr u32 RB = 32 * Q;                                     // rows per block
-    constexpr int NP = (L + 1) / 2;                                // packed accumulators per row
+    constexpr int NP = (L + 1) / 2;                                // pairs of outputs per row
+    constexpr int NPA = (NP + 1) / 2, NPB = NP - NPA;              // role 0: pairs [0, NPA), role 1: [NPA, NP)
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr u32 l = L;
     const u32 m = g.m;
     // this CTA's contiguous range of blocks
     const u64 nb_all = blk_end - blk_begin;
@@ -128,11 +248,16 @@ k_polyphase_ut(const __grid_constant__ UtParams<MAXV> prm, const float *__restri
     if (threadIdx.x == 0) {
         for (u32 s = 0; s < g.nslot; ++s) {
             mbar_init(full + s, 1);
-            mbar_init(empty + s, 1);
+            mbar_init(empty + s, 2);
+            mbar_init(xch + s, 2);
+            mbar_init(staged + s, 2);
         }
         *ticket = 0;
         fence_mbar_init();
     }
+    if (ENVELOPE)
+        for (u32 i = threadIdx.x; i < g.halo_n; i += blockDim.x)
+            halo_taps[i] = __ldg(h + ((g.halo_u0 + i) * L - (L - 1) * g.m));
     __syncthreads();
 
     if (warp == g.warps) {
@@ -140,10 +265,12 @@ k_polyphase_ut(const __grid_constant__ UtParams<MAXV> prm, const float *__restri
         for (u32 n = 0; n < nblk; ++n) {
             const u32 s = n % g.nslot;
             if (n >= g.nslot) mbar_wait(empty + s, ((n / g.nslot) - 1) & 1);
-            float *dst = slots + static_cast<size_t>(s) * g.slot_floats;
+            float *dst = slots + static_cast<size_t>(s) * g.slot_stride;
             const long long x_lo = static_cast<long long>((b0 + n) * RB * m) - g.back;   // sample staged at dst[0]
             const long long x_hi = x_lo + g.slot_floats;
-            if (x_lo >= 0 && static_cast<u64>(x_hi) <= len) {
+            if (g.debug == 2) {                                    // timing experiment: no loads at all
+                if (lane == 0) mbar_arrive(full + s);
+            } else if (x_lo >= 0 && static_cast<u64>(x_hi) <= len) {
                 if (lane == 0) {
                     mbar_expect_tx(full + s, g.slot_floats * 4);
                     tma_bulk_g2s(dst, signal + x_lo, g.slot_floats * 4, full + s);
@@ -173,90 +300,31 @@ k_polyphase_ut(const __grid_constant__ UtParams<MAXV> prm, const float *__restri
     }
     if (warp > g.warps) return;
 
-    // ===== compute warps =====
-    const u32 qstride = 32 * m;
+    // ===== compute warps: tickets are (block, role) pairs; two warps share a block =====
+    const bool profiling = prof != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
+    long long pt = profiling ? clock64() : 0;
     for (;;) {
-        u32 n = 0;
-        if (lane == 0) n = atomicAdd(ticket, 1u);
-        n = __shfl_sync(0xffffffffu, n, 0);
+        u32 t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        const u32 n = t >> 1, role = t & 1;
         if (n >= nblk) break;
-        const u32 s = n % g.nslot;
-        float *slot = slots + static_cast<size_t>(s) * g.slot_floats;
-        mbar_wait(full + s, (n / g.nslot) & 1);
-        const u64 blk = b0 + n;
-        const u64 k0 = blk * RB * l;                               // first output of the block
-
-        f32x2 acc[Q][NP];
-#pragma unroll
-        for (int q = 0; q < Q; ++q)
-#pragma unroll
-            for (int p = 0; p < NP; ++p) acc[q][p] = 0ull;
-        const float *row0 = slot + g.back + lane * m;
-        u32 toff = 0;
-        if (g.debug != 1) {
-            ut_ramp_up<NP, Q, VEC, MAXV>(prm, toff, row0, qstride, acc, std::make_integer_sequence<int, NP - 1>{});
-            ut_segment<0, NP, NP, Q, VEC, MAXV>(prm, prm.cs[NP - 1], prm.ce[0], toff, row0, qstride, acc);
-            ut_ramp_down<NP, Q, VEC, MAXV>(prm, toff, row0, qstride, acc, std::make_integer_sequence<int, NP - 1>{});
-        }
-
-        // r[k0 - 1]: output L-1 of the row in front of the block, k-split over the lanes
-        float halo = 0.f;
-        if (ENVELOPE && k0 > 0) {
-            const float *hw = slot + g.back - m;                   // that row's sample u sits at hw[u]
-            for (u32 i = lane; i < g.halo_n; i += 32) {
-                const u32 u = g.halo_u0 + i;
-                halo = fmaf(__ldg(h + (u * l - (l - 1) * m)), hw[u], halo);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) halo += __shfl_xor_sync(0xffffffffu, halo, o);
-        }
-
-        // ---- epilogue: envelope, transpose through the slot, coalesced stores ----
-        __syncwarp();                                              // every lane is done reading the samples
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            float r[2 * NP];
-#pragma unroll
-            for (int p = 0; p < NP; ++p) unpack2(acc[q][p], r[2 * p], r[2 * p + 1]);
-            float *dst = slot + (q * 32 + lane) * l;
-            if (ENVELOPE) {
-                // the output in front of this row's first: last output of the previous row (lane - 1, or the
-                // previous set of 32 rows' lane 31, or the halo)
-                const float last = r[L - 1];
-                // exchanged through the slot (behind the staged outputs), not with SHFL: warp shuffles in this
-                // loop body make the compiler keep the tap-stream offset in a vector register (LDC instead of LDCU)
-                float *xch = slot + RB * l;
-                xch[q * 32 + lane] = last;
-                __syncwarp();
-                float prev = (q * 32 + lane) == 0 ? halo : xch[q * 32 + lane - 1];
-#pragma unroll
-                for (int j = 0; j < L; ++j) {
-                    dst[j] = envelope2_fast(prev, r[j], cosphi2, inv_sinphi);
-                    prev = r[j];
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < L; ++j) dst[j] = r[j];
-            }
-        }
-        __syncwarp();
-        const u32 nvec = RB * l / 4;                               // RB*l is a multiple of 4
-        for (u32 v = lane; v < nvec; v += 32) {
-            const u64 k = k0 + 4 * v;
-            if (k >= nout) break;
-            float4 val = *reinterpret_cast<const float4 *>(slot + 4 * v);
-            if (ENVELOPE && k == 0) val.x = 0.f;                   // dsp.rs:364: the first sample has no predecessor
-            if (k + 3 < nout) {
-                *reinterpret_cast<float4 *>(out + k) = val;
-            } else {
-                out[k] = val.x;
-                if (k + 1 < nout) out[k + 1] = val.y;
-                if (k + 2 < nout) out[k + 2] = val.z;
-            }
-        }
+        const u32 s = n % g.nslot, parity = (n / g.nslot) & 1;
+        float *slot = slots + static_cast<size_t>(s) * g.slot_stride;
+        if (profiling) { const long long now_ = clock64(); prof[0] += now_ - pt; pt = now_; }
+        mbar_wait(full + s, parity);
+        if (profiling) { const long long now_ = clock64(); prof[1] += now_ - pt; pt = now_; }
+        const u64 k0 = (b0 + n) * RB * L;                          // first output of the block
+        if (role == 0)
+            ut_role<L, 0, NPA, false, Q, VEC, MAXV, ENVELOPE>(prm, g, 0, slot, xch + s, staged + s, parity, role, halo_taps, k0, nout,
+                                                              cosphi2, inv_sinphi, out, lane, profiling, prof, pt);
+        else
+            ut_role<L, NPA, NPB, true, Q, VEC, MAXV, ENVELOPE>(prm, g, static_cast<int>(g.stream_b), slot, xch + s, staged + s, parity,
+                                                               role, halo_taps, k0, nout, cosphi2, inv_sinphi, out, lane, profiling, prof, pt);
         fence_proxy_async();                                       // generic writes before the next bulk copy into the slot
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
+        if (profiling) { const long long now_ = clock64(); prof[5] += now_ - pt; pt = now_; prof[6] += 1; }
     }
 }
 

@@ -111,13 +111,27 @@ int launch_ut_inst(const LaunchCtx &c, const float *signal, u64 len, const float
         prm.cs[p] = up.cs[p];
         prm.ce[p] = up.ce[p];
     }
-    const UtGeom g{up.l, up.m, up.back, up.slot_floats, up.nslot, up.warps, up.halo_u0, up.halo_n, up.debug};
+    const UtGeom g{up.l, up.m, up.back, up.slot_floats, up.nslot, up.warps, up.halo_u0, up.halo_n, up.header_bytes, up.slot_stride, up.stream_b, up.debug};
     auto kern = k_polyphase_ut<static_cast<int>(kUtL), Q, VEC, MAXV, ENV>;
     APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(up.smem_bytes)));
     const unsigned grid = static_cast<unsigned>(std::min<u64>(blk_end - blk_begin, static_cast<u64>(c.sm_count)));
+    unsigned long long *prof = nullptr;
+    if (getenv("APTB200_TILE_PROFILE")) {
+        APT_CUDA(cudaMalloc(&prof, 16 * sizeof(unsigned long long)));
+        APT_CUDA(cudaMemsetAsync(prof, 0, 16 * sizeof(unsigned long long), c.stream));
+    }
     kern<<<grid, 32 * (up.warps + 1), up.smem_bytes, c.stream>>>(prm, signal, len, h, g, nout, blk_begin, blk_end, cosphi2,
-                                                                 1.0f / sinphi, out);
+                                                                 1.0f / sinphi, out, prof);
     APT_CUDA(cudaGetLastError());
+    if (prof) {
+        unsigned long long hp[16];
+        APT_CUDA(cudaStreamSynchronize(c.stream));
+        APT_CUDA(cudaMemcpy(hp, prof, sizeof(hp), cudaMemcpyDeviceToHost));
+        cudaFree(prof);
+        fprintf(stderr, "[ut profile, CTA 0 warp 0: %llu (block, role) units, cycles] ticket %llu wait_full %llu main %llu halo+publish %llu exchange+envelope+stage %llu "
+                        "store+release %llu | plan: q %u warps %u slots %u slot_floats %u chunks %u nvec %u\n",
+                hp[6], hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], up.q, up.warps, up.nslot, up.slot_floats, up.chunks, up.nvec);
+    }
     return APT_OK;
 }
 template <int Q, int VEC, bool ENV>
@@ -148,6 +162,9 @@ int launch_polyphase_ut(const LaunchCtx &c, const float *signal, u64 len, const 
     if (blk_begin >= nblk) return APT_OK;
     if ((reinterpret_cast<uintptr_t>(signal) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || stream.size() != 4ull * up.nvec)
         return fail(APT_ERR_BAD_ARG, "uniform-tap resampler: misaligned buffers or inconsistent plan");
+    if (up.q == 4)
+        return envelope ? launch_ut_vec<4, true>(c, signal, len, h, up, stream, nout, blk_begin, nblk, cosphi2, sinphi, out)
+                        : launch_ut_vec<4, false>(c, signal, len, h, up, stream, nout, blk_begin, nblk, cosphi2, sinphi, out);
     if (up.q == 2)
         return envelope ? launch_ut_vec<2, true>(c, signal, len, h, up, stream, nout, blk_begin, nblk, cosphi2, sinphi, out)
                         : launch_ut_vec<2, false>(c, signal, len, h, up, stream, nout, blk_begin, nblk, cosphi2, sinphi, out);

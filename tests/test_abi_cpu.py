@@ -214,3 +214,89 @@ def test_tile_plan_rejects_shapes_it_cannot_hold(na):
     h = np.ones(14057, np.float32)
     info, _, _, _ = _tile_plan(na, 832, 735, h)          # 11025 Hz: 208 groups > 13 warps -> generic kernel
     assert info is None
+
+
+def _ut_plan(na, l, m, taps):
+    import ctypes as C
+    from noaa_apt_b200._lib import CUtInfo
+    lib = na._lib.load() if hasattr(na, "_lib") else None
+    info = CUtInfo()
+    taps = np.ascontiguousarray(taps, dtype=np.float32)
+    assert lib.apt_ut_plan(l, m, taps.ctypes.data, taps.size, C.byref(info), None, 0) == 0
+    if not info.usable:
+        return info, None
+    stream = np.zeros(4 * info.nvec, dtype=np.float32)
+    assert lib.apt_ut_plan(l, m, taps.ctypes.data, taps.size, C.byref(info), stream.ctypes.data, stream.size) == 0
+    return info, stream
+
+
+@pytest.mark.parametrize("rate,work,l,m", [(48000, 12480, 13, 50), (96000, 12480, 13, 100), (192000, 12480, 13, 200),
+                                           (48000, 20800, 13, 30)])
+def test_uniform_tap_plan_reproduces_fast_resampling(na, rate, work, l, m):
+    """The uniform-tap kernel's host-built plan (roles, chunk ranges per pair, the tap stream in consumption order),
+    emulated with numpy exactly the way the kernel's loop walks it, must give fast_resampling's outputs
+    (dsp.rs:186-289) -- checked against the oracle."""
+    import oracle
+    prof = {12480: "standard", 20800: "slow"}[work]
+    st = na.Settings.profile(prof)
+    f = na.filters.LowpassDcRemoval(na.Freq.hz(st.resample_cutout, rate), st.resample_atten,
+                                    na.Freq.hz(st.resample_delta_freq, rate))
+    f.resample(rate, rate * l)
+    h = f.design()
+    info, stream = _ut_plan(na, l, m, h)
+    assert info.usable and info.l == l and info.m == m and info.np == (l + 1) // 2
+    cs, ce = list(info.cs), list(info.ce)
+    npa = (info.np + 1) // 2
+    assert info.rows_per_block == 32 * info.q and info.back % 4 == 0 and info.slot_floats % 4 == 0
+    assert info.slot_floats >= info.back + (info.rows_per_block - 1) * m + 4 * info.chunks
+    assert info.slot_floats >= info.rows_per_block * l                   # outputs are staged in the slot
+    assert info.warps % 2 == 0 and info.nslot > info.warps // 2 and info.smem_bytes <= 227 * 1024
+    assert info.vec == (4 if m % 4 == 0 else 2 if m % 2 == 0 else 1)
+    assert info.nvec * 16 + 64 <= 32764 - 256                            # fits the kernel-parameter space
+    # the kernel's loop: role by role, segment by segment, 8 taps per (chunk, active pair)
+    taps4 = stream.reshape(-1, 4, 2).astype(np.float64)                 # [record][sample in chunk][output in pair]
+    T = np.zeros((4 * info.chunks, 2 * info.np))                         # rebuilt tap matrix T[u][r]
+    seen = np.zeros_like(T, dtype=bool)
+    rec = 0
+    for pb, npr in ((0, npa), (npa, info.np - npa)):
+        assert 2 * rec == (0 if pb == 0 else info.stream_b)      # stream_b counts float4, a record is two
+        segs = [(cs[pb + a - 1], cs[pb + a], pb, pb + a) for a in range(1, npr)]
+        segs.append((cs[pb + npr - 1], ce[pb], pb, pb + npr))
+        segs += [(ce[pb + a - 1], ce[pb + a], pb + a, pb + npr) for a in range(1, npr)]
+        for c0, c1, p0, p1 in segs:
+            assert c0 <= c1
+            for c in range(c0, c1):
+                for p in range(p0, p1):
+                    assert not seen[4 * c, 2 * p]
+                    T[4 * c:4 * c + 4, 2 * p:2 * p + 2] = taps4[rec]
+                    seen[4 * c:4 * c + 4, 2 * p:2 * p + 2] = True
+                    rec += 1
+    assert rec == info.nvec // 2 and info.nvec % 2 == 0
+    # every tap of the filter appears exactly once: T[u][r] = h[u*l - r*m]
+    off2 = 2 * ((len(h) - 1) // 2)
+    hh = np.asarray(h, dtype=np.float64)
+    for r in range(l):
+        u = np.arange(4 * info.chunks)
+        idx = u * l - r * m
+        ok = (idx >= 0) & (idx <= off2)
+        want = np.where(ok, hh[np.clip(idx, 0, off2)], 0.0)
+        assert np.array_equal(T[:, r], want)
+        assert ((r * m + off2) // l) < 4 * info.chunks                   # the row window covers the last tap
+    assert not T[:, l:].any()                                             # the padding output of an odd L
+    # halo output (r = l-1 of the row in front of a block)
+    assert info.halo_u0 == -(-((l - 1) * m) // l) and info.back >= m - info.halo_u0
+    assert info.halo_u0 + info.halo_n - 1 == ((l - 1) * m + off2) // l
+    x = (np.random.default_rng(0).standard_normal(20000) * 1000).astype(np.float32)
+    ref = oracle.fast_resampling(x, l, m, h)
+    rows = -(-ref.size // l)
+    xpad = np.concatenate([x.astype(np.float64), np.zeros(rows * m + 4 * info.chunks)])
+    win = np.lib.stride_tricks.sliding_window_view(xpad, 4 * info.chunks)[::m][:rows]    # [row][u]
+    out = (win @ T[:, :l]).reshape(-1)[:ref.size]
+    assert np.max(np.abs(out - ref)) <= 1e-6 * np.max(np.abs(ref))
+
+
+def test_uniform_tap_plan_rejects_other_ratios(na):
+    h = np.ones(959, dtype=np.float32)
+    for l, m in ((832, 735), (26, 75), (208, 735)):
+        info, _ = _ut_plan(na, l, m, h)
+        assert not info.usable
