@@ -63,33 +63,76 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock and clock-event (throttle) reasons sampled WHILE a timed region runs (B200_PROFILING.md): NVML through
+    nvidia_ml_py polled every ~1 ms by a thread that only records while `active` is set (timed() sets it around each
+    timed region); `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.sm, self.reasons, self.mx = [], set(), None
+        self.active = False
+        self.running = False
+        self.thread = None
         self.proc = None
+        self.rows = []
+        self.source = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.running = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.running:
+            if self.active:
+                try:
+                    self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                    mask = int(get_reasons(self.handle))
+                    for name, bit in self.REASONS:
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.001)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            if self.active:
+                self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.source == "nvml":
+            self.running = False
+            self.thread.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, polled inside the timed regions"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -106,7 +149,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20 inside the timed regions"}
 
 
 def make_recording(rate, seconds, seed):
@@ -207,21 +250,22 @@ def run_b200(args, rank, local_rank, world):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = sum(d.launch_count for d in decs)
+        sampler.active = True
         e0.record(stream)
         for _ in range(steps):
             fn()
         torch.cuda.synchronize()
         e1.record(stream)
         e1.synchronize()
+        sampler.active = False
         ms = e0.elapsed_time(e1)
         return ms, sum(d.launch_count for d in decs) - l0
 
+    sampler = ClockSampler(local_rank)      # records only inside timed(): the device-resident and the two end-to-end legs
+    sampler.start()
     for _ in range(W):
         produced = step_device()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ms_local, launches = timed(step_device, K)
-    clocks = sampler.stop()
     value, ms_total = sharding.aggregate_throughput(B * n * K, ms_local, dist if dist_on else None, dev)
     ms_step = ms_total / K
 
@@ -255,6 +299,7 @@ def run_b200(args, rank, local_rank, world):
         step_host_pcm16()
     p16_local, _ = timed(step_host_pcm16, K)
     p16_value, p16_total = sharding.aggregate_throughput(B * n * K, p16_local, dist if dist_on else None, dev)
+    clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel: CUDA events on the decoder's stream, per launch ----
     dec.set_profiling(True)

@@ -227,16 +227,16 @@ int apt_tile_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_t
 /* Geometry and tap stream of the uniform-tap resampler (noaa-apt_b200/csrc/kernels_ut.cuh), the kernel that serves
  * fast_resampling + demodulate when L == 13 (48/96/192 kHz -> 12 480 Hz): the taps travel as a kernel parameter.
  * Host logic only.  usable == 0: (l, m, taps) does not fit and the tiled / generic kernels are used.
- * A row q is the L outputs L*q .. L*q+L-1; pair p = outputs 2p, 2p+1; a chunk is 4 consecutive samples of the row's
+ * A row q is the L outputs L*q .. L*q+L-1; pair p = outputs 2p, 2p+1; a chunk is chunk_len (8) consecutive samples of the row's
  * window (sample u of row q is signal[q*M + u]); pair p is active in chunks [cs[p], ce[p]).  Two warps share a block
  * of rows_per_block rows: role 0 owns pairs [0, ceil(np/2)), role 1 the rest.  `stream` (nvec float4 = 4*nvec floats;
  * role 1 starts at float4 index stream_b) holds, in the order the kernel's loop consumes them, per (chunk, active
- * pair) the 8 taps {T[4c][2p], T[4c][2p+1], T[4c+1][2p], ... T[4c+3][2p+1]}, T[u][r] = h[u*L - r*M]; the order is
+ * pair) the 2*chunk_len taps {T[C*c][2p], T[C*c][2p+1], T[C*c+1][2p], ... T[C*c+C-1][2p+1]}, C = chunk_len, T[u][r] = h[u*L - r*M]; the order is
  * ramp-up (pairs pb..pb+a-1 over chunks [cs[pb+a-1], cs[pb+a])), steady (all pairs over [cs[last], ce[pb])), ramp-down
  * (pairs pb+a.. over [ce[pb+a-1], ce[pb+a])). */
 typedef struct apt_ut_info {
     uint32_t usable, l, m, np, q, rows_per_block, vec, back, chunks, slot_floats, slot_stride, nslot, warps, smem_bytes,
-        nvec, stream_b, halo_u0, halo_n;
+        nvec, stream_b, halo_u0, halo_n, chunk_len;
     uint32_t cs[8], ce[8];
 } apt_ut_info;
 int apt_ut_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_ut_info *info, float *stream,

@@ -53,7 +53,7 @@ class CTileInfo(C.Structure):
 class CUtInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("usable", "l", "m", "np", "q", "rows_per_block", "vec", "back", "chunks",
                                           "slot_floats", "slot_stride", "nslot", "warps", "smem_bytes", "nvec",
-                                          "stream_b", "halo_u0", "halo_n")] + [("cs", C.c_uint32 * 8), ("ce", C.c_uint32 * 8)]
+                                          "stream_b", "halo_u0", "halo_n", "chunk_len")] + [("cs", C.c_uint32 * 8), ("ce", C.c_uint32 * 8)]
 
 
 STATUS_CB = C.CFUNCTYPE(None, C.c_float, C.c_char_p, C.c_void_p)

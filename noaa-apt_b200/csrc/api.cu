@@ -760,7 +760,7 @@ extern "C" int apt_ut_plan(uint32_t l, uint32_t m, const float *taps, size_t nta
     info->l = up.l; info->m = up.m; info->np = up.np; info->q = up.q; info->rows_per_block = up.rb; info->vec = up.vec;
     info->back = up.back; info->chunks = up.chunks; info->slot_floats = up.slot_floats; info->slot_stride = up.slot_stride;
     info->nslot = up.nslot; info->warps = up.warps; info->smem_bytes = up.smem_bytes; info->nvec = up.nvec;
-    info->stream_b = up.stream_b; info->halo_u0 = up.halo_u0; info->halo_n = up.halo_n;
+    info->stream_b = up.stream_b; info->halo_u0 = up.halo_u0; info->halo_n = up.halo_n; info->chunk_len = kUtChunk;
     for (int p = 0; p < 8; ++p) {
         info->cs[p] = up.cs[p];
         info->ce[p] = up.ce[p];

@@ -9,10 +9,10 @@
 // of a warp are 32 consecutive rows.  The tap pair (T[u][2p], T[u][2p+1]) is therefore warp-uniform: it is read
 // with LDCU from the kernel-parameter constant bank into uniform registers and used directly as the packed
 // operand of FFMA2 (`FFMA2 R, R.F32, UR.F32x2, R`); the only shared-memory traffic is the thread's own samples
-// (one 4-sample chunk per row per 4*NP FFMA2).  Measured (profiles/r01_microbench_uniform_taps.txt): 104-107
+// (one chunk of CH = 8 samples per row per iteration).  Measured (profiles/r01_microbench_uniform_taps.txt): 104-107
 // FMA/clk/SM, the FFMA2 pipe limit, against 70-84 for shared-memory tap operands.
 //
-// Zero padding.  Pair p only sees samples fx(2p) .. lx(2p+1); the loop over 4-sample chunks is cut into
+// Zero padding.  Pair p only sees samples fx(2p) .. lx(2p+1); the loop over 8-sample chunks is cut into
 // segments with a fixed set of active pairs: ramp-up (pairs 0..a-1 for a = 1..NP-1), steady (all), ramp-down
 // (pairs a..NP-1).  The tap stream in the parameter block is stored in exactly the order the loop consumes it.
 //
@@ -57,62 +57,63 @@ struct UtGeom {
     u32 debug;
 };
 
+constexpr int CH = static_cast<int>(kUtChunk);   // samples per chunk (one loop iteration)
+
+// the CH samples of one chunk of one row, with the widest load the row alignment allows
 template <int VEC>
-__device__ __forceinline__ void ut_load4(const float *p, float (&s)[4]) {
-    if (VEC == 4) {
-        const float4 v = *reinterpret_cast<const float4 *>(p);
-        s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
-    } else if (VEC == 2) {
-        const float2 a = *reinterpret_cast<const float2 *>(p), b = *reinterpret_cast<const float2 *>(p + 2);
-        s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y;
-    } else {
-        s[0] = p[0]; s[1] = p[1]; s[2] = p[2]; s[3] = p[3];
+__device__ __forceinline__ void ut_load_chunk(const float *p, float (&s)[CH]) {
+#pragma unroll
+    for (int i = 0; i < CH; i += 4) {
+        if (VEC == 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(p + i);
+            s[i] = v.x; s[i + 1] = v.y; s[i + 2] = v.z; s[i + 3] = v.w;
+        } else if (VEC == 2) {
+            const float2 a = *reinterpret_cast<const float2 *>(p + i), b = *reinterpret_cast<const float2 *>(p + i + 2);
+            s[i] = a.x; s[i + 1] = a.y; s[i + 2] = b.x; s[i + 3] = b.y;
+        } else {
+            s[i] = p[i]; s[i + 1] = p[i + 1]; s[i + 2] = p[i + 2]; s[i + 3] = p[i + 3];
+        }
     }
 }
 
-// Chunks [cb, ce) with pairs [P0, P1) of a role active.  toff: running float4 index into the tap stream (uniform).
-// `s` holds the samples of chunk cb on entry and of chunk ce on exit (software prefetch: the loads of chunk
-// c+1 are issued before the FFMA2s of chunk c; `clast` clamps the prefetch of the row's last chunk).
+// Chunks [cb, ce) with pairs [P0, P1) of a role active.  toff: running float4 index into the tap stream (uniform);
+// per (chunk, pair) the stream holds CH/2 float4 = the tap pairs of the chunk's CH samples.
 template <int P0, int P1, int NPR, int Q, int VEC, int MAXV>
-__device__ __forceinline__ void ut_segment(const UtParams<MAXV> &prm, u32 cb, u32 ce, u32 clast, int &toff,
-                                           const float *row0, u32 qstride, f32x2 (&acc)[Q][NPR], float (&s)[Q][4]) {
+__device__ __forceinline__ void ut_segment(const UtParams<MAXV> &prm, u32 cb, u32 ce, int &toff, const float *row0,
+                                           u32 qstride, f32x2 (&acc)[Q][NPR]) {
 #pragma unroll 1
     for (u32 c = cb; c < ce; ++c) {
-        float sn[Q][4];
-        const u32 cn = c + 1 < clast ? c + 1 : clast;
+        float s[Q][CH];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) ut_load4<VEC>(row0 + q * qstride + 4 * cn, sn[q]);
+        for (int q = 0; q < Q; ++q) ut_load_chunk<VEC>(row0 + q * qstride + CH * c, s[q]);
 #pragma unroll
         for (int p = P0; p < P1; ++p) {
-            const float4 ta = prm.v[toff + 2 * (p - P0)], tb = prm.v[toff + 2 * (p - P0) + 1];
-            const f32x2 t0 = pack2(ta.x, ta.y), t1 = pack2(ta.z, ta.w), t2 = pack2(tb.x, tb.y), t3 = pack2(tb.z, tb.w);
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                acc[q][p] = fma2(t0, pack2(s[q][0], s[q][0]), acc[q][p]);
-                acc[q][p] = fma2(t1, pack2(s[q][1], s[q][1]), acc[q][p]);
-                acc[q][p] = fma2(t2, pack2(s[q][2], s[q][2]), acc[q][p]);
-                acc[q][p] = fma2(t3, pack2(s[q][3], s[q][3]), acc[q][p]);
+            for (int i = 0; i < CH / 2; ++i) {
+                const float4 t = prm.v[toff + (CH / 2) * (p - P0) + i];
+                const f32x2 t0 = pack2(t.x, t.y), t1 = pack2(t.z, t.w);
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    acc[q][p] = fma2(t0, pack2(s[q][2 * i], s[q][2 * i]), acc[q][p]);
+                    acc[q][p] = fma2(t1, pack2(s[q][2 * i + 1], s[q][2 * i + 1]), acc[q][p]);
+                }
             }
         }
-        toff += 2 * (P1 - P0);
-#pragma unroll
-        for (int q = 0; q < Q; ++q)
-#pragma unroll
-            for (int u = 0; u < 4; ++u) s[q][u] = sn[q][u];
+        toff += (CH / 2) * (P1 - P0);
     }
 }
 
 // One role = a contiguous range of pairs [PB, PB + NPR) of the row's outputs; its loop over chunks is cut into
 // ramp-up (pairs PB..PB+a-1 active), steady (all) and ramp-down (pairs PB+a.. active) segments.
 template <int PB, int NPR, int Q, int VEC, int MAXV, int... A>
-__device__ __forceinline__ void ut_ramp_up(const UtParams<MAXV> &prm, u32 clast, int &toff, const float *row0, u32 qstride,
-                                           f32x2 (&acc)[Q][NPR], float (&s)[Q][4], std::integer_sequence<int, A...>) {
-    (ut_segment<0, A + 1, NPR, Q, VEC, MAXV>(prm, prm.cs[PB + A], prm.cs[PB + A + 1], clast, toff, row0, qstride, acc, s), ...);
+__device__ __forceinline__ void ut_ramp_up(const UtParams<MAXV> &prm, int &toff, const float *row0, u32 qstride,
+                                           f32x2 (&acc)[Q][NPR], std::integer_sequence<int, A...>) {
+    (ut_segment<0, A + 1, NPR, Q, VEC, MAXV>(prm, prm.cs[PB + A], prm.cs[PB + A + 1], toff, row0, qstride, acc), ...);
 }
 template <int PB, int NPR, int Q, int VEC, int MAXV, int... A>
-__device__ __forceinline__ void ut_ramp_down(const UtParams<MAXV> &prm, u32 clast, int &toff, const float *row0, u32 qstride,
-                                             f32x2 (&acc)[Q][NPR], float (&s)[Q][4], std::integer_sequence<int, A...>) {
-    (ut_segment<A + 1, NPR, NPR, Q, VEC, MAXV>(prm, prm.ce[PB + A], prm.ce[PB + A + 1], clast, toff, row0, qstride, acc, s), ...);
+__device__ __forceinline__ void ut_ramp_down(const UtParams<MAXV> &prm, int &toff, const float *row0, u32 qstride,
+                                             f32x2 (&acc)[Q][NPR], std::integer_sequence<int, A...>) {
+    (ut_segment<A + 1, NPR, NPR, Q, VEC, MAXV>(prm, prm.ce[PB + A], prm.ce[PB + A + 1], toff, row0, qstride, acc), ...);
 }
 
 // Everything one warp does for one (block, role): FMA loop over the role's pairs, exchange of the boundary
@@ -139,13 +140,9 @@ __device__ __forceinline__ void ut_role(const UtParams<MAXV> &prm, const UtGeom 
         for (int p = 0; p < NPR; ++p) acc[q][p] = 0ull;
     const float *row0 = slot + g.back + lane * m;
     if (g.debug != 1) {
-        const u32 clast = prm.ce[PB + NPR - 1] - 1;
-        float s[Q][4];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) ut_load4<VEC>(row0 + q * qstride + 4 * prm.cs[PB], s[q]);
-        ut_ramp_up<PB, NPR, Q, VEC, MAXV>(prm, clast, toff, row0, qstride, acc, s, std::make_integer_sequence<int, NPR - 1>{});
-        ut_segment<0, NPR, NPR, Q, VEC, MAXV>(prm, prm.cs[PB + NPR - 1], prm.ce[PB], clast, toff, row0, qstride, acc, s);
-        ut_ramp_down<PB, NPR, Q, VEC, MAXV>(prm, clast, toff, row0, qstride, acc, s, std::make_integer_sequence<int, NPR - 1>{});
+        ut_ramp_up<PB, NPR, Q, VEC, MAXV>(prm, toff, row0, qstride, acc, std::make_integer_sequence<int, NPR - 1>{});
+        ut_segment<0, NPR, NPR, Q, VEC, MAXV>(prm, prm.cs[PB + NPR - 1], prm.ce[PB], toff, row0, qstride, acc);
+        ut_ramp_down<PB, NPR, Q, VEC, MAXV>(prm, toff, row0, qstride, acc, std::make_integer_sequence<int, NPR - 1>{});
     }
     UT_MARK(2)
     // boundary outputs, exchanged through the words behind the slot's samples:

@@ -66,6 +66,7 @@ constexpr u32 kUtPairs = (kUtL + 1) / 2;   // packed accumulators per row
 constexpr u32 kUtMaxVecSmall = 384;    // float4 entries of the tap stream: small / large parameter block
 constexpr u32 kUtMaxVecLarge = 1900;
 constexpr u32 kUtMaxSlots = 24;
+constexpr u32 kUtChunk = 8;            // samples per loop iteration (chunk) of the kernel
 struct UtPlan {
     u32 l, m;
     u32 np;            // pairs of outputs per row = ceil(L/2)
@@ -73,8 +74,8 @@ struct UtPlan {
     u32 rb;            // rows per block = 32*q; a block = rb*L outputs from one contiguous span of the signal
     u32 vec;           // 4/2/1: widest aligned shared-memory load of a row's samples (M % 4 == 0 / M % 2 == 0 / odd)
     u32 back;          // samples staged in front of a block's first row (window of output k0-1), multiple of 4
-    u32 chunks;        // a row touches samples [0, 4*chunks)
-    u32 slot_floats;   // floats of one ring slot = back + (rb-1)*M + 4*chunks, rounded up to 4
+    u32 chunks;        // a row touches samples [0, kUtChunk*chunks)
+    u32 slot_floats;   // floats of one ring slot = back + (rb-1)*M + kUtChunk*chunks, rounded up to 4
     u32 slot_stride;   // floats between slots (slot_floats + 2*rb + 4 exchange words)
     u32 stream_b;      // float4 index of the second role's tap stream (roles: pairs [0, ceil(np/2)) and the rest)
     u32 nslot, warps;  // ring slots, compute warps

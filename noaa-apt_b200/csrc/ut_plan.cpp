@@ -21,8 +21,8 @@ bool make_ut_plan(u32 l, u32 m, const std::vector<float> &taps, UtPlan &up, std:
     u32 cs[8] = {0}, ce[8] = {0};
     for (u32 p = 0; p < np; ++p) {
         const u64 hi = 2 * p + 1 < l ? std::max(lx(2 * p), lx(2 * p + 1)) : lx(2 * p);
-        cs[p] = static_cast<u32>(fx(2 * p) / 4);
-        ce[p] = static_cast<u32>(hi / 4 + 1);
+        cs[p] = static_cast<u32>(fx(2 * p) / kUtChunk);
+        ce[p] = static_cast<u32>(hi / kUtChunk + 1);
         if (p && (cs[p] < cs[p - 1] || ce[p] < ce[p - 1])) return false;
     }
     // two roles share a block: pairs [0, npa) and [npa, np); within a role every pair must have started before
@@ -33,7 +33,7 @@ bool make_ut_plan(u32 l, u32 m, const std::vector<float> &taps, UtPlan &up, std:
     if (chunks > 4096) return false;
 
     // tap stream in consumption order, role by role: ramp-up segments, steady, ramp-down; per (chunk, active
-    // pair) 8 floats {T[4c][2p], T[4c][2p+1], T[4c+1][2p], ... T[4c+3][2p+1]},  T[u][r] = h[u*l - r*m]
+    // pair) 2*CH floats {T[CH*c][2p], T[CH*c][2p+1], T[CH*c+1][2p], ... T[CH*c+CH-1][2p+1]},  T[u][r] = h[u*l - r*m]
     auto tap = [&](u64 u, u32 r) -> float {
         if (r >= l) return 0.f;
         const long long idx = static_cast<long long>(u * l) - static_cast<long long>(static_cast<u64>(r) * m);
@@ -43,9 +43,9 @@ bool make_ut_plan(u32 l, u32 m, const std::vector<float> &taps, UtPlan &up, std:
     auto emit = [&](u32 c0, u32 c1, u32 p0, u32 p1) {
         for (u32 c = c0; c < c1; ++c)
             for (u32 p = p0; p < p1; ++p)
-                for (u32 uu = 0; uu < 4; ++uu) {
-                    stream.push_back(tap(4ull * c + uu, 2 * p));
-                    stream.push_back(tap(4ull * c + uu, 2 * p + 1));
+                for (u32 uu = 0; uu < kUtChunk; ++uu) {
+                    stream.push_back(tap(static_cast<u64>(kUtChunk) * c + uu, 2 * p));
+                    stream.push_back(tap(static_cast<u64>(kUtChunk) * c + uu, 2 * p + 1));
                 }
     };
     auto emit_role = [&](u32 pb, u32 npr) {
@@ -76,7 +76,7 @@ bool make_ut_plan(u32 l, u32 m, const std::vector<float> &taps, UtPlan &up, std:
     for (u32 q : {2u, 1u, 4u}) {
         if (want_q ? q != want_q : q == 4) continue;
         const u32 rb = 32 * q;
-        const u64 slot_floats = (static_cast<u64>(back) + static_cast<u64>(rb - 1) * m + 4ull * chunks + 3) / 4 * 4;
+        const u64 slot_floats = (static_cast<u64>(back) + static_cast<u64>(rb - 1) * m + static_cast<u64>(kUtChunk) * chunks + 3) / 4 * 4;
         const u64 slot_stride = slot_floats + 2 * rb + 4;          // + the exchange words of the two roles
         const u64 slot_bytes = slot_stride * 4;
         if (static_cast<u64>(rb) * l > slot_floats) continue;      // the block's outputs are transposed through its slot

@@ -245,21 +245,22 @@ def test_uniform_tap_plan_reproduces_fast_resampling(na, rate, work, l, m):
     h = f.design()
     info, stream = _ut_plan(na, l, m, h)
     assert info.usable and info.l == l and info.m == m and info.np == (l + 1) // 2
-    cs, ce = list(info.cs), list(info.ce)
+    cs, ce, CH = list(info.cs), list(info.ce), info.chunk_len
+    assert CH % 4 == 0
     npa = (info.np + 1) // 2
     assert info.rows_per_block == 32 * info.q and info.back % 4 == 0 and info.slot_floats % 4 == 0
-    assert info.slot_floats >= info.back + (info.rows_per_block - 1) * m + 4 * info.chunks
+    assert info.slot_floats >= info.back + (info.rows_per_block - 1) * m + CH * info.chunks
     assert info.slot_floats >= info.rows_per_block * l                   # outputs are staged in the slot
     assert info.warps % 2 == 0 and info.nslot > info.warps // 2 and info.smem_bytes <= 227 * 1024
     assert info.vec == (4 if m % 4 == 0 else 2 if m % 2 == 0 else 1)
     assert info.nvec * 16 + 64 <= 32764 - 256                            # fits the kernel-parameter space
-    # the kernel's loop: role by role, segment by segment, 8 taps per (chunk, active pair)
-    taps4 = stream.reshape(-1, 4, 2).astype(np.float64)                 # [record][sample in chunk][output in pair]
-    T = np.zeros((4 * info.chunks, 2 * info.np))                         # rebuilt tap matrix T[u][r]
+    # the kernel's loop: role by role, segment by segment, 2*CH taps per (chunk, active pair)
+    taps4 = stream.reshape(-1, CH, 2).astype(np.float64)                # [record][sample in chunk][output in pair]
+    T = np.zeros((CH * info.chunks, 2 * info.np))                         # rebuilt tap matrix T[u][r]
     seen = np.zeros_like(T, dtype=bool)
     rec = 0
     for pb, npr in ((0, npa), (npa, info.np - npa)):
-        assert 2 * rec == (0 if pb == 0 else info.stream_b)      # stream_b counts float4, a record is two
+        assert rec * CH // 2 == (0 if pb == 0 else info.stream_b)   # stream_b counts float4, a record is CH/2 of them
         segs = [(cs[pb + a - 1], cs[pb + a], pb, pb + a) for a in range(1, npr)]
         segs.append((cs[pb + npr - 1], ce[pb], pb, pb + npr))
         segs += [(ce[pb + a - 1], ce[pb + a], pb + a, pb + npr) for a in range(1, npr)]
@@ -267,21 +268,21 @@ def test_uniform_tap_plan_reproduces_fast_resampling(na, rate, work, l, m):
             assert c0 <= c1
             for c in range(c0, c1):
                 for p in range(p0, p1):
-                    assert not seen[4 * c, 2 * p]
-                    T[4 * c:4 * c + 4, 2 * p:2 * p + 2] = taps4[rec]
-                    seen[4 * c:4 * c + 4, 2 * p:2 * p + 2] = True
+                    assert not seen[CH * c, 2 * p]
+                    T[CH * c:CH * c + CH, 2 * p:2 * p + 2] = taps4[rec]
+                    seen[CH * c:CH * c + CH, 2 * p:2 * p + 2] = True
                     rec += 1
-    assert rec == info.nvec // 2 and info.nvec % 2 == 0
+    assert rec * CH // 2 == info.nvec
     # every tap of the filter appears exactly once: T[u][r] = h[u*l - r*m]
     off2 = 2 * ((len(h) - 1) // 2)
     hh = np.asarray(h, dtype=np.float64)
     for r in range(l):
-        u = np.arange(4 * info.chunks)
+        u = np.arange(CH * info.chunks)
         idx = u * l - r * m
         ok = (idx >= 0) & (idx <= off2)
         want = np.where(ok, hh[np.clip(idx, 0, off2)], 0.0)
         assert np.array_equal(T[:, r], want)
-        assert ((r * m + off2) // l) < 4 * info.chunks                   # the row window covers the last tap
+        assert ((r * m + off2) // l) < CH * info.chunks                   # the row window covers the last tap
     assert not T[:, l:].any()                                             # the padding output of an odd L
     # halo output (r = l-1 of the row in front of a block)
     assert info.halo_u0 == -(-((l - 1) * m) // l) and info.back >= m - info.halo_u0
@@ -289,8 +290,8 @@ def test_uniform_tap_plan_reproduces_fast_resampling(na, rate, work, l, m):
     x = (np.random.default_rng(0).standard_normal(20000) * 1000).astype(np.float32)
     ref = oracle.fast_resampling(x, l, m, h)
     rows = -(-ref.size // l)
-    xpad = np.concatenate([x.astype(np.float64), np.zeros(rows * m + 4 * info.chunks)])
-    win = np.lib.stride_tricks.sliding_window_view(xpad, 4 * info.chunks)[::m][:rows]    # [row][u]
+    xpad = np.concatenate([x.astype(np.float64), np.zeros(rows * m + CH * info.chunks)])
+    win = np.lib.stride_tricks.sliding_window_view(xpad, CH * info.chunks)[::m][:rows]    # [row][u]
     out = (win @ T[:, :l]).reshape(-1)[:ref.size]
     assert np.max(np.abs(out - ref)) <= 1e-6 * np.max(np.abs(ref))
 
