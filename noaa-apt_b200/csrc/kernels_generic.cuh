@@ -33,7 +33,7 @@ __device__ __forceinline__ float envelope2_fast(float prev, float curr, float co
     const float sq = fmaf(prev, prev, curr * curr);
     const float arg = fmaf(-(prev * curr), cosphi2, sq);
     float root;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(root) : "f"(arg));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(root) : "f"(arg));   // one MUFU.SQRT; denormal arguments (|x| < 1e-19) flush to 0
     return root * inv_sinphi;
 }
 

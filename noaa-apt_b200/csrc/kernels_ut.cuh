@@ -123,12 +123,16 @@ __device__ __forceinline__ void ut_role(const UtParams<MAXV> &prm, const UtGeom 
                                         u64 *staged_bar, u32 parity, u32 role, const float *halo_taps, u64 k0, u64 nout,
                                         float cosphi2, float inv_sinphi, float *__restrict__ out, u32 lane, bool profiling,
                                         unsigned long long *prof, long long &pt) {
+#ifdef APTB200_UT_PROFILE
 #define UT_MARK(slot_)                                   \
     if (profiling) {                                     \
         const long long now_ = clock64();                \
         prof[slot_] += now_ - pt;                        \
         pt = now_;                                       \
     }
+#else
+#define UT_MARK(slot_)
+#endif
     constexpr u32 RB = 32 * Q;
     constexpr int JB = 2 * PB;                                       // first output (phase) of this role
     constexpr int JN = (2 * NPR < L - JB) ? 2 * NPR : L - JB;        // number of real outputs
@@ -298,8 +302,14 @@ k_polyphase_ut(const __grid_constant__ UtParams<MAXV> prm, const float *__restri
     if (warp > g.warps) return;
 
     // ===== compute warps: tickets are (block, role) pairs; two warps share a block =====
+    // per-phase cycle counters of CTA 0 / warp 0: compiled in with -DAPTB200_UT_PROFILE only (APTB200_TILE_PROFILE=1 prints them)
+#ifdef APTB200_UT_PROFILE
     const bool profiling = prof != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
     long long pt = profiling ? clock64() : 0;
+#else
+    const bool profiling = false;
+    long long pt = 0;
+#endif
     for (;;) {
         u32 t = 0;
         if (lane == 0) t = atomicAdd(ticket, 1u);
@@ -308,9 +318,13 @@ k_polyphase_ut(const __grid_constant__ UtParams<MAXV> prm, const float *__restri
         if (n >= nblk) break;
         const u32 s = n % g.nslot, parity = (n / g.nslot) & 1;
         float *slot = slots + static_cast<size_t>(s) * g.slot_stride;
+#ifdef APTB200_UT_PROFILE
         if (profiling) { const long long now_ = clock64(); prof[0] += now_ - pt; pt = now_; }
+#endif
         mbar_wait(full + s, parity);
+#ifdef APTB200_UT_PROFILE
         if (profiling) { const long long now_ = clock64(); prof[1] += now_ - pt; pt = now_; }
+#endif
         const u64 k0 = (b0 + n) * RB * L;                          // first output of the block
         if (role == 0)
             ut_role<L, 0, NPA, false, Q, VEC, MAXV, ENVELOPE>(prm, g, 0, slot, xch + s, staged + s, parity, role, halo_taps, k0, nout,
@@ -321,7 +335,9 @@ k_polyphase_ut(const __grid_constant__ UtParams<MAXV> prm, const float *__restri
         fence_proxy_async();                                       // generic writes before the next bulk copy into the slot
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
+#ifdef APTB200_UT_PROFILE
         if (profiling) { const long long now_ = clock64(); prof[5] += now_ - pt; pt = now_; prof[6] += 1; }
+#endif
     }
 }
 
