@@ -59,6 +59,33 @@ __device__ __forceinline__ T block_scan_incl(T v, T identity, Op op, T *s_warp /
     return v;
 }
 
+// Inclusive SUFFIX scan over the CTA: thread t gets op over the values of threads t..THREADS-1.
+template <int THREADS, typename T, typename Op>
+__device__ __forceinline__ T block_scan_incl_rev(T v, T identity, Op op, T *s_warp /* THREADS/32 entries */) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr u32 NW = (THREADS + 31) / 32;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T t = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o < 32) v = op(v, t);
+    }
+    if (lane == 0) s_warp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        T w = lane < NW ? s_warp[lane] : identity;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const T t = __shfl_down_sync(0xffffffffu, w, o);
+            if (lane + o < 32) w = op(w, t);
+        }
+        if (lane < NW) s_warp[lane] = w;
+    }
+    __syncthreads();
+    if (warp + 1 < NW) v = op(v, s_warp[warp + 1]);
+    __syncthreads();
+    return v;
+}
+
 template <int THREADS, int CHUNK>
 __global__ void __launch_bounds__(THREADS, CHUNK <= 10 ? 4 : 2)
 k_roots(const float *__restrict__ corr, u64 ncorr, u32 dist, u32 *__restrict__ root_list,
@@ -100,32 +127,39 @@ k_roots(const float *__restrict__ corr, u64 ncorr, u32 dist, u32 *__restrict__ r
     const u32 hi = min(lo + CHUNK, dist);   // chunk [lo, hi) of the block (may be empty)
     float va[CHUNK], vb[CHUNK];
     float cmax_a = NEG, cmax_b = NEG;
+    if (CHUNK % 4 == 0 && (dist & 3) == 0 && lo + CHUNK <= dist) {
+        // whole chunk inside the block and 16-byte aligned: vector loads, no bounds selects
+#pragma unroll
+        for (int c = 0; c < CHUNK; c += 4) {
+            const float4 x = *reinterpret_cast<const float4 *>(a + lo + c), y = *reinterpret_cast<const float4 *>(a + dist + lo + c);
+            va[c] = x.x; va[c + 1] = x.y; va[c + 2] = x.z; va[c + 3] = x.w;
+            vb[c] = y.x; vb[c + 1] = y.y; vb[c + 2] = y.z; vb[c + 3] = y.w;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < CHUNK; ++c) {
+            const u32 i = lo + c;
+            va[c] = i < hi ? a[i] : NEG;
+            vb[c] = i < hi ? a[dist + i] : NEG;
+        }
+    }
 #pragma unroll
     for (int c = 0; c < CHUNK; ++c) {
-        const u32 i = lo + c;
-        va[c] = i < hi ? a[i] : NEG;
-        vb[c] = i < hi ? a[dist + i] : NEG;
         cmax_a = fmaxf(cmax_a, va[c]);
         cmax_b = fmaxf(cmax_b, vb[c]);
     }
     auto fmx = [](float x, float y) { return fmaxf(x, y); };
-    // prefix maxima over the next block's chunks; suffix maxima over this block's chunks (scan in reversed order:
-    // thread THREADS-1-t carries chunk t)
+    // prefix maxima over the next block's chunks, suffix maxima over this block's chunks; each thread then needs the
+    // neighbour's inclusive value (chunks < tid of the next block, chunks > tid of this block)
     const float pre_incl = block_scan_incl<THREADS>(cmax_b, NEG, fmx, s_wf);
-    // a[] is no longer needed (the chunks are in registers): reuse it to reverse the thread order
+    const float suf_incl = block_scan_incl_rev<THREADS>(cmax_a, NEG, fmx, s_wf);
+    __syncthreads();                         // a[] is no longer needed (the chunks are in registers): reuse it
+    float *s_pre = sm, *s_suf = sm + THREADS;
+    s_pre[tid] = pre_incl;
+    s_suf[tid] = suf_incl;
     __syncthreads();
-    float *s_rev = sm;                       // THREADS floats
-    s_rev[THREADS - 1 - tid] = cmax_a;
-    __syncthreads();
-    const float rev_in = s_rev[tid];
-    const float suf_incl_rev = block_scan_incl<THREADS>(rev_in, NEG, fmx, s_wf);
-    s_rev[THREADS - 1 - tid] = suf_incl_rev; // back to chunk order: s_rev[t] = max of chunks >= t
-    __syncthreads();
-    const float right = tid + 1 < THREADS ? s_rev[tid + 1] : NEG;                   // chunks > tid of this block
-    __syncthreads();
-    s_rev[tid] = pre_incl;
-    __syncthreads();
-    const float left_excl = tid > 0 ? s_rev[tid - 1] : NEG;                         // chunks < tid of the next block
+    const float left_excl = tid > 0 ? s_pre[tid - 1] : NEG;
+    const float right = tid + 1 < THREADS ? s_suf[tid + 1] : NEG;
 
     // prefix maxima inside the next block's chunk, then walk this block's chunk right-to-left
     float pm[CHUNK];
@@ -457,9 +491,20 @@ k_gather_rows(const float *__restrict__ f, const u32 *__restrict__ positions,
     const u32 n_rows = positions ? result->n_rows : fixed_rows;
     for (u32 j = blockIdx.x; j < n_rows; j += gridDim.x) {
         const u64 p = positions ? positions[j] : static_cast<u64>(j) * row;
-        for (u32 c = threadIdx.x; c < px; c += blockDim.x) {
-            const float v = __ldg(f + p + static_cast<u64>(c) * dec);
-            out[static_cast<u64>(j) * px + c] = (j == 0 && c == 0) ? 0.f : v;
+        // 9 independent loads in flight per thread (px = 2080 = 8.1 x 256): the kernel is latency-bound otherwise
+        constexpr u32 U = 9;
+        for (u32 c0 = threadIdx.x; c0 < px; c0 += U * blockDim.x) {
+            float v[U];
+#pragma unroll
+            for (u32 u = 0; u < U; ++u) {
+                const u32 c = c0 + u * blockDim.x;
+                v[u] = c < px ? __ldg(f + p + static_cast<u64>(c) * dec) : 0.f;
+            }
+#pragma unroll
+            for (u32 u = 0; u < U; ++u) {
+                const u32 c = c0 + u * blockDim.x;
+                if (c < px) out[static_cast<u64>(j) * px + c] = (j == 0 && c == 0) ? 0.f : v[u];
+            }
         }
     }
 }

@@ -24,13 +24,13 @@ inline unsigned grid_for(u64 n, unsigned per_block, int sms) {
     return static_cast<unsigned>(std::max<u64>(1, std::min(blocks, cap)));
 }
 
-template <int CHUNK>
+template <int CHUNK, int THREADS = 512>
 int roots_with_chunk(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32 nblocks, u32 *root_list,
                      u32 *root_count, SyncResult *result, const PickScratch *sc) {
     const size_t smem = 2ull * dist * sizeof(float);
-    auto kern = k_roots<512, CHUNK>;
+    auto kern = k_roots<THREADS, CHUNK>;
     APT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<nblocks, 512, smem, c.stream>>>(corr, ncorr, dist, root_list, root_count, result,
+    kern<<<nblocks, THREADS, smem, c.stream>>>(corr, ncorr, dist, root_list, root_count, result,
                                             sc ? sc->block_off : nullptr, sc ? sc->ticket : nullptr);
     APT_CUDA(cudaGetLastError());
     return APT_OK;
