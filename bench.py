@@ -15,6 +15,7 @@ stream), cpu_baseline (oracle on the host cores), e2e (host buffers through the 
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -323,13 +324,13 @@ def run_b200(args, rank, local_rank, world):
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, from the committed ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "r01_ncu_all_kernels_metrics.json")) as f:
             for m in json.load(f):
-                if "k_polyphase_ws" in m["kernel"] and abs(args.seconds - 900.0) < 1e-6 and rate == 48000:
+                if "k_polyphase_ut" in m["kernel"] and abs(args.seconds - 900.0) < 1e-6 and rate == 48000:
                     traffic = (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) * 1e6
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_kind,
-                "algorithmic_bytes": alg_bytes, "kernel_ms": kernel_ms.get(dom),
+                "algorithmic_bytes": alg_bytes, "kernel_ms": kernel_ms.get(dom), "kernel_name": "k_polyphase_ut" if 12480 // math.gcd(rate, 12480) == 13 else "k_polyphase_ws / k_polyphase_generic",
                 "all_kernels_ms": kernel_ms}
 
     line = None

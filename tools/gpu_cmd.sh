@@ -1,7 +1,5 @@
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for v in lp4 lp5 lp6; do
-  cp noaa-apt_b200/libaptb200_$v.so noaa-apt_b200/libaptb200.so
-  echo "== $v"; timeout 100 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | grep -o '"ms_per_step": [0-9.]*, "higher\|"all_kernels_ms": {[^}]*}'
-done
-cp noaa-apt_b200/libaptb200_lp4.so noaa-apt_b200/libaptb200.so
-echo "== batch 16"; timeout 200 python bench.py --steps 10 --warmup 3 --batch 16 --no-cpu-baseline 2>&1 | grep -o '"value": [0-9.]*, "unit"' | head -1
+bash tools/ncu_capture.sh
+timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -c 900 gpurun_out/bench_final.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 400 gpurun_out/bench_ref.json
+timeout 400 python bench.py --workload c3 --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; tail -c 1200 gpurun_out/bench_c3.json
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
