@@ -213,13 +213,23 @@ int launch_lowpass_corr(const LaunchCtx &c, const float *e, u64 n, const float *
                         float *corr) {
     if (n == 0) return APT_OK;
     LpTaps t{};
-    for (u32 j = 0; j < ntaps && j < 64; ++j) t.c[j] = taps_host[j];
+    auto tap = [&](long long j) { return j >= 0 && j < static_cast<long long>(ntaps) ? taps_host[j] : 0.f; };
+    for (int i = 0; i < 32; ++i) {
+        t.a_even[i] = make_float2(tap(2 * i), tap(2 * i - 1));
+        t.a_odd[i] = make_float2(tap(2 * i + 1), tap(2 * i));
+    }
     const u64 ncorr = n > 38ull * pw ? n - 38ull * pw : 0;
     const u64 ntiles = (n + kLpTile - 1) / kLpTile;
-    const unsigned grid = static_cast<unsigned>(std::min<u64>(ntiles, static_cast<u64>(c.sm_count) * 6));
-    if (ntaps == 37 && pw == 3) k_lowpass_corr<37, 3><<<grid, 256, 0, c.stream>>>(e, n, ncorr, t, f, corr);
-    else if (ntaps == 43 && pw == 4) k_lowpass_corr<43, 4><<<grid, 256, 0, c.stream>>>(e, n, ncorr, t, f, corr);
-    else if (ntaps == 61 && pw == 5) k_lowpass_corr<61, 5><<<grid, 256, 0, c.stream>>>(e, n, ncorr, t, f, corr);
+    // persistent: exactly the resident CTAs, each walks its tiles with the next tile's loads in flight
+    auto launch = [&](auto kern) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        const unsigned grid = static_cast<unsigned>(std::min<u64>(ntiles, static_cast<u64>(c.sm_count) * per_sm));
+        kern<<<grid, 256, 0, c.stream>>>(e, n, ncorr, t, f, corr);
+    };
+    if (ntaps == 37 && pw == 3) launch(k_lowpass_corr<37, 3>);
+    else if (ntaps == 43 && pw == 4) launch(k_lowpass_corr<43, 4>);
+    else if (ntaps == 61 && pw == 5) launch(k_lowpass_corr<61, 5>);
     else return fail(APT_ERR_BAD_ARG, "no fused low-pass/correlation kernel for %u taps, pixel width %u", ntaps, pw);
     APT_CUDA(cudaGetLastError());
     return APT_OK;
