@@ -1,5 +1,7 @@
-// Tiled polyphase resampler fused with the envelope demodulator -- the hot kernel of the path
-// (fast_resampling dsp.rs:186-289 + demodulate dsp.rs:350-383), written for sm_100a.
+// Tiled polyphase resampler fused with the envelope demodulator (fast_resampling dsp.rs:186-289 + demodulate
+// dsp.rs:350-383), written for sm_100a.  It served L = 13 until kernels_ut.cuh replaced it there (92 -> 62 us) and
+// still serves other small interpolation factors (L <= 13 groups, e.g. L = 26); the mbarrier / TMA / packed-fp32
+// helpers below are shared by both.
 //
 // Formulation.  y[k] = sum_x h[x*L - k*M] * X[x].  Outputs k and k + P_out (P_out = lcm(8, L)) use the
 // same taps on inputs shifted by P_in = P_out*M/L, so per "group" g (outputs 8g..8g+7 of a super-period)

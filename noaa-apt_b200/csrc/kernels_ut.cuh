@@ -1,16 +1,16 @@
 // Polyphase resampler + envelope with the taps in the CONSTANT BANK (kernel parameter), read through the
-// uniform datapath -- the hot kernel of the path for small L (48/96/192 kHz -> 12 480 Hz has L = 13).
+// uniform datapath -- the hot kernel of the path for L = 13 (48/96/192 kHz -> 12 480 Hz).
 // fast_resampling dsp.rs:186-289 + demodulate dsp.rs:350-383.
 //
 // Formulation.  Output k = L*q + r ("row" q, phase r < L) is
 //     y[L*q + r] = sum_u h[u*L - r*M] * X[q*M + u]
 // i.e. every row uses the SAME L tap sets T[u][r] = h[u*L - r*M] on a window that moves by M samples per row.
-// A thread owns Q rows x all L outputs of each (NP = ceil(L/2) packed fp32x2 accumulators per row); the 32 lanes
-// of a warp are 32 consecutive rows.  The tap pair (T[u][2p], T[u][2p+1]) is therefore warp-uniform: it is read
-// with LDCU from the kernel-parameter constant bank into uniform registers and used directly as the packed
-// operand of FFMA2 (`FFMA2 R, R.F32, UR.F32x2, R`); the only shared-memory traffic is the thread's own samples
-// (one chunk of CH = 8 samples per row per iteration).  Measured (profiles/r01_microbench_uniform_taps.txt): 104-107
-// FMA/clk/SM, the FFMA2 pipe limit, against 70-84 for shared-memory tap operands.
+// A thread owns Q rows x the output PAIRS (2p, 2p+1) of its role (one packed fp32x2 accumulator per pair and row);
+// the 32 lanes of a warp are 32 consecutive rows.  The tap pair (T[u][2p], T[u][2p+1]) is therefore warp-uniform:
+// it is read with LDCU from the kernel-parameter constant bank into uniform registers and used directly as the
+// packed operand of FFMA2 (`FFMA2 R, R.F32, UR.F32x2, R`); the only shared-memory traffic is the thread's own
+// samples (one chunk of CH = 8 samples per row per loop iteration).  In isolation the form reaches 104-107 FMA/clk/SM,
+// the FFMA2 pipe limit, against 70-84 for shared-memory tap operands (profiles/r01_microbench_uniform_taps.txt).
 //
 // Zero padding.  Pair p only sees samples fx(2p) .. lx(2p+1); the loop over 8-sample chunks is cut into
 // segments with a fixed set of active pairs: ramp-up (pairs 0..a-1 for a = 1..NP-1), steady (all), ramp-down
@@ -19,10 +19,13 @@
 // Pipeline.  One persistent CTA per SM owns a contiguous range of blocks (block = 32*Q rows = 32*Q*L outputs,
 // whose input is ONE contiguous span of the signal: no duplication in shared memory).  A producer warp streams
 // blocks into a ring of NSLOT shared-memory slots with one cp.async.bulk (TMA) per block, completion on a
-// full mbarrier; W compute warps take blocks off the ring in order (shared-memory ticket), compute, turn
-// (r[k-1], r[k]) into the envelope, transpose the block's outputs through the (now dead) slot and store
-// coalesced float4; an empty mbarrier hands the slot back.  Warps are not coupled by any CTA-wide barrier.
-// r[k0-1] for the first output of a block is a k-split dot product over the warp (taps from global memory).
+// `full` mbarrier.  TWO compute warps share a block: role 0 owns the first half of the output pairs, role 1 the
+// rest; warps draw (block, role) tickets from a shared-memory counter, so nothing couples the warps CTA-wide.
+// After its FMA loop a warp publishes the one output its partner's envelope needs (role boundary / row boundary)
+// in the words behind the slot, the pair meets on the `xch` mbarrier (nobody reads the samples any more), both
+// compute their envelopes (dsp.rs:373), transpose them through the dead slot, meet on `staged`, store half of the
+// block each as coalesced float4, and release the slot through the `empty` mbarrier (count 2).  r[k0-1] for the
+// first output of a block is a dot product of role 1 split over its lanes (taps of output L-1 staged in shared memory).
 #pragma once
 
 

@@ -222,8 +222,11 @@ int launch_lowpass_corr(const LaunchCtx &c, const float *e, u64 n, const float *
     const u64 ntiles = (n + kLpTile - 1) / kLpTile;
     // persistent: exactly the resident CTAs, each walks its tiles with the next tile's loads in flight
     auto launch = [&](auto kern) {
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        static const int per_sm = [&] {          // per instantiation (generic lambda); the same on every B200
+            int v = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, 256, 0) != cudaSuccess || v < 1) v = 2;
+            return v;
+        }();
         const unsigned grid = static_cast<unsigned>(std::min<u64>(ntiles, static_cast<u64>(c.sm_count) * per_sm));
         kern<<<grid, 256, 0, c.stream>>>(e, n, ncorr, t, f, corr);
     };
