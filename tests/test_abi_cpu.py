@@ -231,7 +231,7 @@ def _ut_plan(na, l, m, taps):
 
 
 @pytest.mark.parametrize("rate,work,l,m", [(48000, 12480, 13, 50), (96000, 12480, 13, 100), (192000, 12480, 13, 200),
-                                           (48000, 20800, 13, 30)])
+                                           (48000, 20800, 13, 30), (96000, 20800, 13, 60)])
 def test_uniform_tap_plan_reproduces_fast_resampling(na, rate, work, l, m):
     """The uniform-tap kernel's host-built plan (roles, chunk ranges per pair, the tap stream in consumption order),
     emulated with numpy exactly the way the kernel's loop walks it, must give fast_resampling's outputs
