@@ -293,7 +293,8 @@ def test_uniform_tap_plan_reproduces_fast_resampling(na, rate, work, l, m):
     xpad = np.concatenate([x.astype(np.float64), np.zeros(rows * m + CH * info.chunks)])
     win = np.lib.stride_tricks.sliding_window_view(xpad, CH * info.chunks)[::m][:rows]    # [row][u]
     out = (win @ T[:, :l]).reshape(-1)[:ref.size]
-    assert np.max(np.abs(out - ref)) <= 1e-6 * np.max(np.abs(ref))
+    # the oracle sums up to 428 taps per output in f32; this emulation sums in f64 (the taps were checked exactly above)
+    assert np.max(np.abs(out - ref)) <= 5e-6 * np.max(np.abs(ref))
 
 
 def test_uniform_tap_plan_rejects_other_ratios(na):
