@@ -179,9 +179,10 @@ def test_decode_matches_oracle(rate, seconds):
     assert ctx.log[0][1] == "Resampling to 12480" and ctx.log[3][1] == "Syncing"
 
 
-@pytest.mark.parametrize("profile", ["fast", "slow"])
-def test_decode_other_profiles(profile):
-    rate = 48000
+@pytest.mark.parametrize("rate,profile", [(48000, "fast"), (48000, "slow"), (96000, "slow")])
+def test_decode_other_profiles(rate, profile):
+    # 48 kHz fast: L = 26 (tiled kernel); slow: L = 13 with the large tap-stream parameter block; 96 kHz slow: the
+    # uniform-tap kernel at its shared-memory limit (13 slots, 231.8 KB)
     x = synth.apt_signal(rate, 12, seed=11)
     settings = na.Settings.profile(profile)
     os_ = oracle.default_settings()
