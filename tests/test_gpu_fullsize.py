@@ -1,0 +1,171 @@
+"""GPU parity at the REAL sizes of BASELINE.json's configs, and on the reference's own recording.
+
+The small-size tests (test_gpu_parity.py) cannot see what depends on size: the persistent-grid partitioning of
+the resampler, u32 indices, the picker's scratch capacity and its cluster / cooperative launches, the default
+chunked upload.  Here every BASELINE config is decoded at (or near) its full size and compared with the CPU
+oracle: sync positions equal exactly, rows within 1e-5 of the stage's max |value| (decode.rs:43-162).
+
+    c2  configs[1]  one 48 kHz x 900 s recording
+    c3  configs[2]  96 kHz, long enough for the DEFAULT chunked upload (> 64 Mi samples), f32 and PCM16; 1 hour
+    c4  configs[3]  64 recordings on 64 decoders (= 64 CUDA streams) of one GPU, each against the oracle
+    c1  configs[0]  excerpts of the reference's test/test_11025hz.wav (tests/golden/make_wav_excerpt.py)
+"""
+import os
+
+import numpy as np
+import pytest
+
+import noaa_apt_b200 as na
+from noaa_apt_b200 import synth
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def nerr(got, ref):
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    scale = float(np.max(np.abs(ref))) if ref.size else 1.0
+    return float(np.max(np.abs(got.astype(np.float64) - ref.astype(np.float64)))) / (scale or 1.0)
+
+
+@pytest.fixture(scope="module")
+def rec48():
+    """Four distinct 48 kHz x 900 s recordings (PCM16) and their oracle decodes."""
+    pcms = [synth.apt_pcm16(48000, 900, seed=s) for s in range(4)]
+    refs = [oracle.decode_steps(p.astype(np.float32), 48000) for p in pcms]
+    return pcms, refs
+
+
+@pytest.fixture(scope="module")
+def rec96():
+    return synth.apt_pcm16(96000, 900, seed=1)
+
+
+def test_c2_full_size_48khz_900s(rec48):
+    pcms, refs = rec48
+    x = pcms[0].astype(np.float32)
+    ref, st = refs[0]
+    with na.Decoder(48000, na.Settings(), max_samples=x.size) as dec:
+        got = dec.decode(x, sync=True)
+        pos = dec.last_sync()
+        counts = dec.last_counts()
+        env = dec.read_stage("demodulated")
+    assert counts["n_work"] == st["demodulated"].size == 11_231_991
+    assert np.array_equal(pos, st["sync_pos"])
+    assert nerr(env, st["demodulated"]) <= TOL
+    assert got.size == ref.size and got.size // 2080 >= 1790
+    assert nerr(got, ref) <= TOL
+    # the call the Rust shim binds (rust/decode.rs -> apt_decode) on an ordinary pageable buffer, PCM16 too
+    got2 = na.decode(na.Context(), na.Settings(), x, 48000, True)
+    assert got2.size == ref.size and nerr(got2, ref) <= TOL
+    got3 = na.decode(na.Context(), na.Settings(), pcms[0], 48000, True)
+    assert got3.size == ref.size and nerr(got3, ref) <= TOL
+
+
+def test_c3_shaped_default_chunked_upload_96khz_720s(rec96):
+    # 69.1 M samples > 64 Mi: apt_decoder_create picks the chunked, overlapped upload by itself (no env override)
+    pcm = rec96[: 96000 * 720]
+    assert pcm.size > (64 << 20)
+    x = pcm.astype(np.float32)
+    ref, st = oracle.decode_steps(x, 96000)
+    with na.Decoder(96000, na.Settings(), max_samples=x.size) as dec:
+        got = dec.decode(x)
+        assert np.array_equal(dec.last_sync(), st["sync_pos"])
+        assert nerr(dec.read_stage("demodulated"), st["demodulated"]) <= TOL
+        got16 = dec.decode(pcm)
+        assert np.array_equal(dec.last_sync(), st["sync_pos"])
+    assert got.size == ref.size and nerr(got, ref) <= TOL
+    assert got16.size == ref.size and nerr(got16, ref) <= TOL
+    # device-resident input of the same recording: one launch over the whole signal
+    import torch
+    xd = torch.from_numpy(x).cuda()
+    od = torch.empty(ref.size + 2080 * 8, dtype=torch.float32, device="cuda")
+    with na.Decoder(96000, na.Settings(), max_samples=x.size) as dec:
+        dec.submit_device(xd.data_ptr(), na._lib.F32, x.size, True, od.data_ptr(), od.numel())
+        n = dec.wait()
+        assert np.array_equal(dec.last_sync(), st["sync_pos"])
+    assert n == ref.size and nerr(od[:n].cpu().numpy(), ref) <= TOL
+
+
+def test_c3_one_hour_96khz(rec96):
+    # 345.6 M samples (1.38 GB as f32): N_w = 44.9 M, ~7200 rows, ~230 k roots -- the picker's large-size path.
+    # 900 s = 1800 whole lines and 2 160 000 carrier cycles, so the repetition is a continuous APT signal.
+    pcm = np.tile(rec96, 4)
+    x = pcm.astype(np.float32)
+    ref, st = oracle.decode_steps(x, 96000)
+    with na.Decoder(96000, na.Settings(), max_samples=x.size) as dec:
+        got = dec.decode(pcm)                         # host PCM16, chunked
+        pos = dec.last_sync()
+    assert np.array_equal(pos, st["sync_pos"])
+    assert got.size == ref.size and got.size // 2080 >= 7190
+    assert nerr(got, ref) <= TOL
+
+
+def test_c4_shaped_64_recordings_on_64_streams(rec48):
+    import torch
+    pcms, refs = rec48
+    n = pcms[0].size
+    xs = [torch.from_numpy(p.astype(np.float32)).pin_memory() for p in pcms]
+    bound = na.decode_len_bound(n, 48000)
+    decs = [na.Decoder(48000, na.Settings(), max_samples=n) for _ in range(64)]
+    outs = [torch.empty(bound, dtype=torch.float32).pin_memory() for _ in range(64)]
+    try:
+        for rnd in range(2):                           # second round: every decoder reused
+            for k, d in enumerate(decs):
+                d.submit_host_ptr(xs[(k + rnd) % 4].data_ptr(), na._lib.F32, n, True, outs[k].data_ptr(), bound)
+            for k, d in enumerate(decs):
+                got_n = d.wait()
+                ref, st = refs[(k + rnd) % 4]
+                assert got_n == ref.size
+                assert np.array_equal(d.last_sync(), st["sync_pos"]), f"decoder {k} round {rnd}"
+                assert nerr(outs[k][:got_n].numpy(), ref) <= TOL
+    finally:
+        for d in decs:
+            d.close()
+
+
+def test_c4_decode_batch_entry_point(rec48):
+    # apt_decode_batch: 12 recordings, feeder threads, completion-order reaping (api.cu)
+    pcms, refs = rec48
+    sigs = [pcms[k % 4] for k in range(12)]
+    outs, statuses = na.decode_batch(sigs, 48000, na.Settings(), True, devices=[0], streams_per_device=4)
+    assert statuses == [0] * 12
+    for k, got in enumerate(outs):
+        ref = refs[k % 4][0]
+        assert got.size == ref.size and nerr(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("name", ["start", "dup"])
+def test_c1_reference_recording_excerpts(name):
+    """The reference's own test/test_11025hz.wav (test/test.sh:45): noise, skipped frames, and the duplicate sync
+    position the `while` at decode.rs:244 pushes -- through the CUDA path, against the oracle."""
+    g = np.load(os.path.join(GOLDEN, "test_11025hz_excerpts.npz"))
+    pcm = g[f"pcm_{name}"]
+    x = oracle.pcm16_to_f32(pcm)
+    ref, st = oracle.decode_steps(x, 11025)
+    assert np.array_equal(st["sync_pos"], g[f"sync_{name}"])          # drift guard of the oracle itself
+    if name == "dup":
+        assert int(np.diff(st["sync_pos"].astype(np.int64)).min()) == 0
+    with na.Decoder(11025, na.Settings(), max_samples=x.size) as dec:
+        got = dec.decode(pcm)
+        assert np.array_equal(dec.last_sync(), st["sync_pos"])
+        assert nerr(dec.read_stage("demodulated"), st["demodulated"]) <= TOL
+        assert nerr(dec.read_stage("filtered"), st["filtered"]) <= TOL
+        got_f32 = dec.decode(x)
+    assert got.size == ref.size and nerr(got, ref) <= TOL
+    assert got_f32.size == ref.size and nerr(got_f32, ref) <= TOL
+    # other profiles on the real recording (§8 f4: 11025 Hz x fast / slow through decode())
+    for profile in ("fast", "slow"):
+        settings = na.Settings.profile(profile)
+        os_ = oracle.default_settings()
+        os_.work_rate, os_.resample_atten = settings.work_rate, settings.resample_atten
+        os_.resample_delta_freq, os_.resample_cutout = settings.resample_delta_freq, settings.resample_cutout
+        os_.demodulation_atten = settings.demodulation_atten
+        rp, sp = oracle.decode_steps(x, 11025, os_)
+        with na.Decoder(11025, settings, max_samples=x.size) as dec:
+            gp = dec.decode(x)
+            assert np.array_equal(dec.last_sync(), sp["sync_pos"]), profile
+        assert gp.size == rp.size and nerr(gp, rp) <= TOL, profile

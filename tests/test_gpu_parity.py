@@ -200,8 +200,10 @@ def test_decode_pcm16_equals_f32():
     pcm = synth.apt_pcm16(rate, 12, seed=5)
     a = na.decode(na.Context(), na.Settings(), pcm, rate, True)
     b = na.decode(na.Context(), na.Settings(), pcm.astype(np.float32), rate, True)
-    # the PCM16 and f32 loads may run different kernels (different summation order), same tolerance
-    assert a.size == b.size and nerr(a, b) <= TOL
+    # both against the oracle fed with the `as f32` cast of wav.rs:37 (not against each other)
+    ref = oracle.decode(oracle.pcm16_to_f32(pcm), rate)
+    assert a.size == ref.size and nerr(a, ref) <= TOL
+    assert b.size == ref.size and nerr(b, ref) <= TOL
 
 
 def test_decode_no_sync():
