@@ -1,19 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the APT decode hot path on B200 (BASELINE.json metric).
+"""bench.py -- throughput of the APT decode hot path on B200 (BASELINE.json metric: input Msamples/s decoded).
 
-One "step" = one pass of decode() (resample -> envelope -> low-pass -> sync -> rows) over one
-synthetic recording per GPU.  Workload at every N: BASELINE.json configs[1], a single synthetic
-48 kHz, 15-min, 2.4 kHz-subcarrier APT recording (43.2 M samples) per GPU ("weak" scaling: each
-rank decodes its own recording, no collective on the data path).
+One "step" = one pass of decode() (resample -> envelope -> low-pass -> sync -> rows) over one batch of synthetic
+recordings per GPU.  Default workload at every N: BASELINE.json configs[3] -- a batch of 64 independent 48 kHz, 15-min,
+2.4 kHz-subcarrier APT recordings per GPU, one per CUDA stream; at N GPUs that is configs[4] (512 recordings over 8
+GPUs): "weak" scaling, every rank decodes its own 64 recordings, no collective on the data path.  The single-recording
+configuration (configs[1], the one the roofline kernel is quoted on) is measured in the same run and reported under
+"single_recording" and "roofline"; `--workload c2` / `c3` make configs[1] / configs[2] the timed workload instead.
 
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference        # CPU arm: the oracle port of the Rust reference
+    python bench.py --impl reference        # CPU arm: the oracle port of the Rust reference on the host cores
 
-JSON keys beyond the base contract: roofline (dominant kernel, CUDA-event timed on the decoder's
-stream), cpu_baseline (oracle on the host cores), e2e (host buffers through the C ABI), clocks.
+JSON keys beyond the base contract: roofline (dominant kernel, CUDA-event timed on the decoder's stream), cpu_baseline
+(oracle on the host cores), e2e (pageable host buffers through the C-ABI batch call), e2e_apt_decode (one apt_decode()
+call per recording: what rust/decode.rs binds), e2e_pinned_decoders (explicit decoder objects, pinned buffers), clocks,
+parity (the rows and sync positions of what was timed, checked against the CPU oracle).
 """
 import argparse
+import ctypes as C
 import json
 import math
 import os
@@ -21,6 +26,7 @@ import subprocess
 import sys
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -30,6 +36,7 @@ if ROOT not in sys.path:
 
 METRIC = "input_msamples_per_s_decoded"
 UNIT = "Msamples/s"
+TOL = 1e-5
 
 
 def parse_args():
@@ -40,15 +47,15 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rate", type=int, default=48000, help="input sample rate (Hz)")
     ap.add_argument("--seconds", type=float, default=900.0, help="recording length")
-    ap.add_argument("--cpu-seconds", type=float, default=300.0,
-                    help="length of the recording slice the CPU arms decode per step")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
-                    help="c2: BASELINE configs[1], one 48 kHz 15-min recording per GPU (default, the metric's config); "
-                         "c3: configs[2], one 96 kHz 10-hour recording (a 900-s synthetic recording repeated 40x), "
-                         "uploaded in overlapping chunks for the end-to-end number")
-    ap.add_argument("--batch", type=int, default=1,
-                    help="recordings decoded per GPU per step, one per CUDA stream (BASELINE configs[3]: 64)")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3"],
+                    help="c4 (default): BASELINE configs[3]/[4], a batch of --batch recordings per GPU, one per CUDA stream; "
+                         "c2: configs[1], one 48 kHz 15-min recording per GPU; c3: configs[2], one 96 kHz 10-hour recording "
+                         "(a 900-s synthetic recording repeated 40x), uploaded in overlapping chunks")
+    ap.add_argument("--batch", type=int, default=64, help="recordings per GPU per step (c4)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arms (0: all available, at most one per recording)")
+    ap.add_argument("--cpu-seconds", type=float, default=0.0, help="cap the recording length the CPU arms decode (0: full length)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the single-recording and other-rate measurements")
     return ap.parse_args()
 
 
@@ -65,10 +72,11 @@ def measured_peaks():
 
 class ClockSampler:
     """SM clock and clock-event (throttle) reasons sampled WHILE a timed region runs (B200_PROFILING.md): NVML through
-    nvidia_ml_py polled every ~1 ms by a thread that only records while `active` is set (timed() sets it around each
+    nvidia_ml_py polled at 20 Hz by a thread that only records while `active` is set (timed() sets it around each
     timed region); `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
 
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+    PERIOD = 0.05
 
     def __init__(self, index):
         self.index = index
@@ -98,7 +106,7 @@ class ClockSampler:
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
@@ -106,20 +114,23 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def _poll(self):
+    def _sample(self):
         n = self.nvml
         get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            mask = int(get_reasons(self.handle))
+            for name, bit in self.REASONS:
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _poll(self):
         while self.running:
             if self.active:
-                try:
-                    self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
-                    mask = int(get_reasons(self.handle))
-                    for name, bit in self.REASONS:
-                        if mask & bit:
-                            self.reasons.add(name)
-                except Exception:
-                    pass
-            time.sleep(0.001)
+                self._sample()
+            time.sleep(self.PERIOD)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -131,7 +142,8 @@ class ClockSampler:
             self.running = False
             self.thread.join(timeout=1)
             return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
-                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, polled inside the timed regions"}
+                    "reasons": sorted(self.reasons), "samples": len(self.sm),
+                    "source": "nvml, polled at 20 Hz inside the timed regions"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
@@ -150,7 +162,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20 inside the timed regions"}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 50 inside the timed regions"}
 
 
 def make_recording(rate, seconds, seed):
@@ -158,39 +170,98 @@ def make_recording(rate, seconds, seed):
     return synth.apt_pcm16(rate, seconds, seed=seed)
 
 
-def cpu_arm(pcm, rate, steps, warmup):
-    """Times the CPU oracle (C restatement of the Rust reference, 1 thread like the reference)."""
+def make_recordings(rate, seconds, seeds):
+    with ThreadPoolExecutor(max_workers=len(seeds)) as ex:
+        return list(ex.map(lambda s: make_recording(rate, seconds, s), seeds))
+
+
+def workload_string(args, B, repeat=1):
+    if args.workload == "c3":
+        return (f"single synthetic {args.rate} Hz {args.seconds * repeat:g}-s APT recording (BASELINE configs[2]; 900-s recording "
+                f"x{repeat}; host upload chunked with filter-length overlap)")
+    if args.workload == "c2" or B == 1:
+        return f"single synthetic {args.rate} Hz {args.seconds:g}-s APT recording per GPU (BASELINE configs[1])"
+    return (f"batch of {B} independent synthetic {args.rate} Hz {args.seconds:g}-s APT recordings per GPU, one per CUDA stream "
+            f"(BASELINE configs[3]; {B}/GPU x 8 GPUs = configs[4])")
+
+
+def available_cpus():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_arm(signals, rate, jobs, threads, steps, warmup):
+    """Times the CPU oracle (C restatement of the Rust reference; one decode is single-threaded like the reference,
+    `threads` independent recordings run side by side).  One step = `jobs` recordings.  Returns Msamples/s, s/step."""
     import oracle
-    x = pcm.astype(np.float32)
-    for _ in range(warmup):
-        oracle.decode(x, rate)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        oracle.decode(x, rate)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return x.size / dt / 1e6, dt
+    oracle.lib()
+
+    def one(k):
+        return oracle.decode(signals[k % len(signals)], rate).size
+
+    def step(ex):
+        return list(ex.map(one, range(jobs)))
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        for _ in range(warmup):
+            step(ex)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step(ex)
+        dt = (time.perf_counter() - t0) / max(steps, 1)
+    total = sum(signals[k % len(signals)].size for k in range(jobs))
+    return total / dt / 1e6, dt
+
+
+def cpu_setup(args, B):
+    """Signals, jobs per step and threads of a CPU arm: the same recordings (full length unless --cpu-seconds caps it),
+    one per thread, at most one batch per step."""
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))      # the CPU arm may use every core of the box
+    except Exception:
+        pass
+    cpus = available_cpus()
+    threads = args.cpu_threads if args.cpu_threads > 0 else cpus
+    threads = max(1, min(threads, B))
+    jobs = threads if B > 1 else 1
+    return threads, jobs
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port: the Rust crate cannot be built
-    here) on the host cores, same config/metric, each step a bounded slice of the workload."""
+    """--impl reference: the reference's CPU algorithm (oracle port: the Rust crate cannot be built here) on the host
+    cores with every thread it can use (one recording per thread), same config/metric; each step decodes a bounded
+    sample of the GPU arm's per-step workload: `jobs` of its recordings, full length."""
     if rank != 0:
         return
-    pcm = make_recording(args.rate, min(args.cpu_seconds, args.seconds), seed=0)
-    value, dt = cpu_arm(pcm, args.rate, args.steps, min(args.warmup, 1))
+    B = 1 if args.workload in ("c2", "c3") else max(args.batch, 1)
+    if args.workload == "c3":
+        args.rate = 96000
+    threads, jobs = cpu_setup(args, B)
+    seconds = min(args.cpu_seconds, args.seconds) if args.cpu_seconds > 0 else args.seconds
+    pcms = make_recordings(args.rate, seconds, list(range(min(B, 4))))
+    sigs = [p.astype(np.float32) for p in pcms]
+    value, dt = cpu_arm(sigs, args.rate, jobs, threads, args.steps, min(args.warmup, 1))
+    repeat = 40 if args.workload == "c3" else 1
+    sample = (f"{jobs} of the {B * world} recordings of a step, {seconds:g} s each" + ("" if seconds == args.seconds else
+              f" (first {seconds:g} s of {args.seconds:g})") + f", one per thread on {threads} threads; C restatement of the "
+              f"single-threaded Rust decode (no Rust toolchain in the image)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"single synthetic {args.rate} Hz {args.seconds:g}-s APT recording (BASELINE configs[1])",
-                   "profile": "standard"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"first {min(args.cpu_seconds, args.seconds):g} s of the recording per step; "
-                                   f"C restatement of the single-threaded Rust decode (no Rust toolchain in the image)",
-                         "host_cores_available": os.cpu_count()},
+        "config": {"workload": workload_string(args, B, repeat), "profile": "standard"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "host_cores_available": available_cpus()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def nerr(got, ref):
+    scale = float(np.max(np.abs(ref))) if ref.size else 1.0
+    return float(np.max(np.abs(got.astype(np.float64) - ref.astype(np.float64)))) / (scale or 1.0)
 
 
 def run_b200(args, rank, local_rank, world):
@@ -200,7 +271,10 @@ def run_b200(args, rank, local_rank, world):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    lib = na._lib.load()
+    numa_bound = bool(lib.apt_bind_thread_to_device(local_rank))      # this process and its pinned buffers: the GPU's NUMA node
     dist_on = world > 1
+    dist = None
     if dist_on:
         os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
         import torch.distributed as dist
@@ -210,13 +284,16 @@ def run_b200(args, rank, local_rank, world):
     repeat = 1
     if args.workload == "c3":
         args.rate, args.seconds, args.batch, repeat = 96000, 900.0, 1, 40
+    if args.workload == "c2":
+        args.batch = 1
     rate, K, W, B = args.rate, args.steps, max(args.warmup, 3), max(args.batch, 1)
     dev = f"cuda:{local_rank}"
     settings = na.Settings()
-    # B recordings per GPU, one decoder (= one CUDA stream + workspaces) each; up to 4 distinct seeds are
-    # generated and replicated into separate device buffers
+    cset = settings.to_c()
+    # B recordings per GPU, one decoder (= one CUDA stream + workspaces) each; up to 4 distinct seeds are generated and
+    # replicated into separate device buffers
     n_seeds = min(B, 4)
-    pcms = [make_recording(rate, args.seconds, seed=rank * 4 + k) for k in range(n_seeds)]
+    pcms = make_recordings(rate, args.seconds, [rank * 4 + k for k in range(n_seeds)])
     if repeat > 1:
         # 900 s = 1800 whole lines and 2 160 000 carrier cycles: the repetition is a continuous APT signal
         pcms = [np.tile(p, repeat) for p in pcms]
@@ -224,20 +301,7 @@ def run_b200(args, rank, local_rank, world):
     decs = [na.Decoder(rate, settings, max_samples=n, device=local_rank) for _ in range(B)]
     dec = decs[0]
     bound = dec.out_bound(n)
-
-    # ---- device-resident arm ("value"): the Signals (f32, wav.rs:37) already in HBM ----
-    x_hosts = [torch.from_numpy(p.astype(np.float32)).pin_memory() for p in pcms]
-    x_devs = [x_hosts[k % n_seeds].to(dev) if k < n_seeds else x_hosts[k % n_seeds].to(dev).clone() for k in range(B)]
-    out_devs = [torch.empty(bound, dtype=torch.float32, device=dev) for _ in range(B)]
-    stream = torch.cuda.ExternalStream(dec.stream, device=local_rank)
-
-    def step_device():
-        for k in range(B):
-            decs[k].submit_device(x_devs[k].data_ptr(), na._lib.F32, n, True, out_devs[k].data_ptr(), bound)
-        got = 0
-        for k in range(B):
-            got = decs[k].wait()
-        return got
+    F32, PCM16 = na._lib.F32, na._lib.PCM16
 
     def barrier():
         torch.cuda.synchronize()
@@ -245,8 +309,12 @@ def run_b200(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        """K steps bracketed by barrier + synchronize; device time between two events recorded on decoder 0's
+    sampler = ClockSampler(local_rank)      # records only inside timed(): every timed leg
+    sampler.start()
+    stream = torch.cuda.ExternalStream(dec.stream, device=local_rank)
+
+    def timed(fn, steps, drain=None):
+        """`steps` steps bracketed by barrier + synchronize; device time between two events recorded on decoder 0's
         stream after/before full-device synchronisation, so it spans the work of every stream."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -255,60 +323,116 @@ def run_b200(args, rank, local_rank, world):
         e0.record(stream)
         for _ in range(steps):
             fn()
+        if drain:
+            drain()
         torch.cuda.synchronize()
         e1.record(stream)
         e1.synchronize()
         sampler.active = False
-        ms = e0.elapsed_time(e1)
-        return ms, sum(d.launch_count for d in decs) - l0
+        return e0.elapsed_time(e1), sum(d.launch_count for d in decs) - l0
 
-    sampler = ClockSampler(local_rank)      # records only inside timed(): the device-resident and the two end-to-end legs
-    sampler.start()
+    def throughput(samples, ms_local):
+        return sharding.aggregate_throughput(samples, ms_local, dist if dist_on else None, dev)
+
+    # ---- device-resident arm ("value"): the Signals (f32, wav.rs:37) already in HBM.  Pipelined: decoder k takes its
+    #      next recording as soon as its previous one is done, the other B-1 streams keep the GPU busy meanwhile ----
+    x_f32 = [p.astype(np.float32) for p in pcms]                         # ordinary pageable arrays (what apt_decode gets)
+    x_devs = [torch.from_numpy(x_f32[k % n_seeds]).to(dev) for k in range(B)]
+    out_devs = [torch.empty(bound, dtype=torch.float32, device=dev) for _ in range(B)]
+    pending = [False] * B
+    produced = [0] * B
+
+    def step_device():
+        for k in range(B):
+            if pending[k]:
+                produced[k] = decs[k].wait()
+            decs[k].submit_device(x_devs[k].data_ptr(), F32, n, True, out_devs[k].data_ptr(), bound)
+            pending[k] = True
+
+    def drain():
+        for k in range(B):
+            if pending[k]:
+                produced[k] = decs[k].wait()
+                pending[k] = False
+
     for _ in range(W):
-        produced = step_device()
-    ms_local, launches = timed(step_device, K)
-    value, ms_total = sharding.aggregate_throughput(B * n * K, ms_local, dist if dist_on else None, dev)
+        step_device()
+    drain()
+    ms_local, launches = timed(step_device, K, drain)
+    value, ms_total = throughput(B * n * K, ms_local)
     ms_step = ms_total / K
+    sync_dev = [decs[k].last_sync() for k in range(n_seeds)]
+    rows_dev = [out_devs[k][: produced[k]].cpu().numpy() for k in range(n_seeds)]
 
-    # ---- end-to-end arm: host buffers through the reference-facing call (H2D + D2H inside) ----
-    out_hosts = [torch.empty(bound, dtype=torch.float32).pin_memory() for _ in range(B)]
+    # ---- end-to-end arm ("e2e"): the reference-facing batch call on ordinary PAGEABLE host buffers, H2D + D2H inside ----
+    outs = [np.zeros(bound, dtype=np.float32) for _ in range(B)]        # zeros: the pages exist before the timed region
+    sig_ptrs = (C.c_void_p * B)(*[x_f32[k % n_seeds].ctypes.data for k in range(B)])
+    out_ptrs = (C.c_void_p * B)(*[o.ctypes.data for o in outs])
+    lens = (C.c_uint64 * B)(*([n] * B))
+    caps = (C.c_uint64 * B)(*([bound] * B))
+    nouts = (C.c_uint64 * B)()
+    statuses = (C.c_int * B)()
+    dev_arr = (C.c_int * 1)(local_rank)
+    streams = 1 if B == 1 else 3
 
-    def step_host():
+    def step_batch(ptrs=sig_ptrs, fmt=F32):
+        rc = lib.apt_decode_batch(ptrs, fmt, lens, B, rate, C.byref(cset), 1, out_ptrs, caps, nouts, statuses, dev_arr, 1, streams)
+        if rc != 0:
+            raise SystemExit(f"apt_decode_batch failed: {rc} {lib.apt_last_error().decode()}")
+
+    step_batch()
+    e2e_local, _ = timed(step_batch, K)
+    e2e_value, e2e_total = throughput(B * n * K, e2e_local)
+    rows_e2e = [outs[k][: nouts[k]].copy() for k in range(n_seeds)]
+
+    # same with the WAV's PCM16 samples (apt_decode_pcm16's path: half the PCIe bytes, the `as f32` of wav.rs:37 on the GPU)
+    p_ptrs = (C.c_void_p * B)(*[pcms[k % n_seeds].ctypes.data for k in range(B)])
+    step_batch(p_ptrs, PCM16)
+    p16_local, _ = timed(lambda: step_batch(p_ptrs, PCM16), K)
+    p16_value, p16_total = throughput(B * n * K, p16_local)
+    rows_p16 = [outs[k][: nouts[k]].copy() for k in range(n_seeds)]
+
+    # one apt_decode() per recording -- the call rust/decode.rs binds: pageable Vec<f32> in, rows out, the decoder parked
+    # in the library between calls
+    nout1 = C.c_uint64(0)
+    cb0 = na._lib.STATUS_CB()
+    n_single = min(B, 16)
+
+    def step_apt_decode():
+        for k in range(n_single):
+            rc = lib.apt_decode(x_f32[k % n_seeds].ctypes.data, n, rate, C.byref(cset), 1, outs[k].ctypes.data, bound,
+                                C.byref(nout1), cb0, None)
+            if rc != 0:
+                raise SystemExit(f"apt_decode failed: {rc} {lib.apt_last_error().decode()}")
+
+    step_apt_decode()
+    k1 = max(1, min(K, 10))
+    one_local, _ = timed(step_apt_decode, k1)
+    one_value, one_total = throughput(n_single * n * k1, one_local)
+    lib.apt_cache_clear()
+
+    # explicit decoder objects with pinned buffers (round 1's e2e), pipelined like the device-resident arm
+    x_pin = [torch.from_numpy(x_f32[k]).pin_memory() for k in range(n_seeds)]
+    out_pin = [torch.empty(bound, dtype=torch.float32).pin_memory() for _ in range(B)]
+
+    def step_pinned():
         for k in range(B):
-            decs[k].submit_host_ptr(x_hosts[k % n_seeds].data_ptr(), na._lib.F32, n, True, out_hosts[k].data_ptr(), bound)
-        got = 0
-        for k in range(B):
-            got = decs[k].wait()
-        return got
+            if pending[k]:
+                decs[k].wait()
+            decs[k].submit_host_ptr(x_pin[k % n_seeds].data_ptr(), F32, n, True, out_pin[k].data_ptr(), bound)
+            pending[k] = True
 
-    for _ in range(2):
-        produced_host = step_host()
-    e2e_local, _ = timed(step_host, K)
-    e2e_value, e2e_total = sharding.aggregate_throughput(B * n * K, e2e_local, dist if dist_on else None, dev)
-    e2e_ms = e2e_total / K
-
-    # same, handing over the WAV's PCM16 samples (apt_decode_pcm16's path: the `as f32` of wav.rs:37 runs on the GPU)
-    p_hosts = [torch.from_numpy(p.copy()).pin_memory() for p in pcms]
-
-    def step_host_pcm16():
-        for k in range(B):
-            decs[k].submit_host_ptr(p_hosts[k % n_seeds].data_ptr(), na._lib.PCM16, n, True, out_hosts[k].data_ptr(), bound)
-        for k in range(B):
-            decs[k].wait()
-
-    for _ in range(2):
-        step_host_pcm16()
-    p16_local, _ = timed(step_host_pcm16, K)
-    p16_value, p16_total = sharding.aggregate_throughput(B * n * K, p16_local, dist if dist_on else None, dev)
+    step_pinned()
+    drain()
+    pin_local, _ = timed(step_pinned, K, drain)
+    pin_value, pin_total = throughput(B * n * K, pin_local)
     clocks = sampler.stop()
 
-    # ---- roofline of the dominant kernel: CUDA events on the decoder's stream, per launch ----
+    # ---- roofline of the dominant kernel: CUDA events on the decoder's stream, per launch, one recording alone ----
     dec.set_profiling(True)
     acc = {}
-    prof_steps = min(K, 10)
-    for _ in range(prof_steps):
-        # one recording alone on the GPU: the per-kernel times are not disturbed by the other streams
-        dec.submit_device(x_devs[0].data_ptr(), na._lib.F32, n, True, out_devs[0].data_ptr(), bound)
+    for _ in range(10):
+        dec.submit_device(x_devs[0].data_ptr(), F32, n, True, out_devs[0].data_ptr(), bound)
         dec.wait()
         for name, ms in dec.kernel_times_ms():
             acc.setdefault(name, []).append(ms)
@@ -320,49 +444,105 @@ def run_b200(args, rank, local_rank, world):
     dom = "resample_envelope"
     alg_bytes = 4 * n + 4 * n_work                      # read every input once, write every e once
     achieved = alg_bytes / (kernel_ms[dom] * 1e-3) / 1e9 if dom in kernel_ms else None
-    traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_all_kernels_metrics.json")) as f:
+    traffic, traffic_source = None, None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
+        tp = os.path.join("profiles", "r02_ncu_kernels_metrics.json")
+        with open(os.path.join(ROOT, tp)) as f:
             for m in json.load(f):
-                if "k_polyphase_ut" in m["kernel"] and abs(args.seconds - 900.0) < 1e-6 and rate == 48000:
+                if "k_polyphase_ut" in m["kernel"] and abs(args.seconds - 900.0) < 1e-6 and rate == 48000 and repeat == 1:
                     traffic = (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) * 1e6
+                    traffic_source = tp + " (committed ncu capture of the same kernel and input, not this run)"
     except Exception:
         pass
+    step_bytes = 4 * n + 4 * int(produced[0])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_kind,
-                "algorithmic_bytes": alg_bytes, "kernel_ms": kernel_ms.get(dom), "kernel_name": "k_polyphase_ut" if 12480 // math.gcd(rate, 12480) == 13 else "k_polyphase_ws / k_polyphase_generic",
-                "all_kernels_ms": kernel_ms}
+                "frac": achieved / peak if achieved else None, "traffic": traffic, "traffic_source": traffic_source,
+                "peak_source": peak_kind, "algorithmic_bytes": alg_bytes, "kernel_ms": kernel_ms.get(dom),
+                "kernel_name": "k_polyphase_ut" if 12480 // math.gcd(rate, 12480) == 13 else "k_polyphase_ph / k_polyphase_ws",
+                "all_kernels_ms": kernel_ms,
+                "whole_decode": {"algorithmic_bytes": step_bytes, "ms": sum(kernel_ms.values()),
+                                 "frac_of_peak": step_bytes / (sum(kernel_ms.values()) * 1e-3) / 1e9 / peak}}
+
+    # ---- the single-recording configuration (configs[1]) and the other input rates, measured in the same run ----
+    single, rates = None, None
+    if not args.no_extras and args.workload == "c4":
+        def one_device():
+            dec.submit_device(x_devs[0].data_ptr(), F32, n, True, out_devs[0].data_ptr(), bound)
+            dec.wait()
+
+        for _ in range(3):
+            one_device()
+        s_ms, _ = timed(one_device, K)
+        _, s_tot = throughput(n * K, s_ms)
+        single = {"workload": "single synthetic 48000 Hz 900-s recording per GPU (BASELINE configs[1]), one decode at a time",
+                  "value": world * n * K / (s_tot * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": s_tot / K}
+        if world == 1:
+            rates = other_rates(na, lib, cset, local_rank, timed, K)
+
+    # ---- parity of what was timed: rows and sync positions against the CPU oracle (outside the timed regions) ----
+    import oracle
+    check = n <= 200_000_000                 # the 10-hour recording of c3 would keep the oracle busy for minutes
+    refs = []
+    if check:
+        with ThreadPoolExecutor(max_workers=n_seeds) as ex:
+            refs = list(ex.map(lambda x: oracle.decode_steps(x, rate), x_f32))
+    worst = 0.0
+    for k in range(len(refs)):
+        ref, st = refs[k]
+        if not np.array_equal(sync_dev[k], st["sync_pos"]):
+            raise SystemExit(f"bench: sync positions of recording {k} differ from the oracle")
+        for name, rows in (("device", rows_dev[k]), ("e2e", rows_e2e[k]), ("e2e_pcm16", rows_p16[k])):
+            if rows.size != ref.size:
+                raise SystemExit(f"bench: {name} rows of recording {k}: {rows.size} values, oracle {ref.size}")
+            err = nerr(rows, ref)
+            worst = max(worst, err)
+            if err > TOL:
+                raise SystemExit(f"bench: {name} rows of recording {k} differ from the oracle: {err:.3e} > {TOL}")
+    parity = {"checked": f"{n_seeds} distinct recordings x (device-resident, e2e f32, e2e PCM16) rows + sync positions vs the "
+                         f"CPU oracle on the full recording", "sync_positions_equal": True, "max_normalised_error": worst,
+              "tolerance": TOL} if check else {"checked": "skipped: recording too long for the oracle inside the bench "
+                                                          "(tests/test_gpu_fullsize.py covers the chunked path)"}
 
     line = None
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            sl = pcms[0][: int(min(args.cpu_seconds, args.seconds * repeat) * rate)]
-            v, dt = cpu_arm(sl, rate, steps=3, warmup=1)
-            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"first {sl.size / rate:g} s of the same recording, 3 timed decodes; C restatement of the "
-                             f"single-threaded Rust decode", "host_cores_available": os.cpu_count()}
+            threads, jobs = cpu_setup(args, B)
+            sigs = x_f32 if args.cpu_seconds <= 0 else [x[: int(args.cpu_seconds * rate)] for x in x_f32]
+            if repeat > 1:
+                sigs = [x[: 900 * rate] for x in x_f32]
+            v, dt = cpu_arm(sigs, rate, jobs, threads, steps=3, warmup=1)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{jobs} of the step's recordings ({sigs[0].size / rate:g} s each), one per thread on {threads} "
+                             f"threads, 3 timed passes; C restatement of the single-threaded Rust decode",
+                   "host_cores_available": available_cpus()}
+        elif world > 1:
+            cpu = {"omitted": "measured at N=1 only (rank 0), see the N=1 line"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": (f"single synthetic {rate} Hz {args.seconds * repeat:g}-s APT recording "
-                                    f"(BASELINE configs[2]; 900-s recording x{repeat}; host upload chunked with "
-                                    f"filter-length overlap)" if args.workload == "c3" else
-                                    f"single synthetic {rate} Hz {args.seconds:g}-s APT recording per GPU "
-                                    f"(BASELINE configs[1])" if B == 1 else
-                                    f"batch of {B} synthetic {rate} Hz {args.seconds:g}-s APT recordings per GPU, one per "
-                                    f"CUDA stream (BASELINE configs[3])"),
+            "config": {"workload": workload_string(args, B, repeat),
                        "profile": "standard", "recordings_per_gpu": B, "samples_per_recording": int(n),
-                       "work_samples": int(n_work), "rows": int(produced // 2080), "sync_roots": int(counts["n_roots"]),
-                       "l2": f"inputs_exceed_l2 ({4 * n / 1e6:.1f} MB f32 input per recording > 126 MB L2)",
-                       "sharding": "one recording per GPU, no collective"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(4 * n * B),
-                    "d2h_bytes_per_step": int((4 * produced_host + 32) * B), "input": "pinned host f32 Signal"},
+                       "work_samples": int(n_work), "rows": int(produced[0] // 2080), "sync_roots": int(counts["n_roots"]),
+                       "l2": f"inputs_exceed_l2 ({4 * n * B / 1e6:.1f} MB of f32 input per GPU and step > 126 MB L2)",
+                       "sharding": "independent recordings, no collective; recording -> stream of its rank's GPU",
+                       "numa_bound": numa_bound},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_total / K, "h2d_bytes_per_step": int(4 * n * B),
+                    "d2h_bytes_per_step": int(sum(4 * int(v) + 32 for v in nouts)),
+                    "call": f"apt_decode_batch (C ABI), pageable host f32 buffers in and out, {streams} stream(s) per GPU"},
             "e2e_pcm16": {"value": p16_value, "unit": UNIT, "ms_per_step": p16_total / K, "h2d_bytes_per_step": int(2 * n * B),
-                          "input": "pinned host int16 (the WAV's samples); cast on the device"},
+                          "call": "apt_decode_batch, pageable int16 (the WAV's samples); cast on the device"},
+            "e2e_apt_decode": {"value": one_value, "unit": UNIT, "ms_per_recording": one_total / k1 / n_single,
+                               "call": "apt_decode() once per recording, pageable buffers, decoder parked in the library "
+                                       "between calls (what rust/decode.rs binds)"},
+            "e2e_pinned_decoders": {"value": pin_value, "unit": UNIT, "ms_per_step": pin_total / K,
+                                    "call": "apt_decoder_submit_host on pinned buffers, one decoder per recording"},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "single_recording": single,
+            "other_rates": rates,
+            "parity": parity,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
@@ -373,6 +553,54 @@ def run_b200(args, rank, local_rank, world):
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+def other_rates(na, lib, cset, device, timed, K):
+    """north_star asks for 11025 / 48000 / 96000 Hz: one 900-s recording each, device-resident and through apt_decode()."""
+    import torch
+    out = {}
+    for rate in (11025, 96000):
+        pcm = make_recording(rate, 900.0, seed=0)
+        x = pcm.astype(np.float32)
+        n = x.size
+        xd = torch.from_numpy(x).cuda(device)
+        with na.Decoder(rate, na.Settings(), max_samples=n, device=device) as dec:
+            bound = dec.out_bound(n)
+            od = torch.empty(bound, dtype=torch.float32, device=f"cuda:{device}")
+
+            def one():
+                dec.submit_device(xd.data_ptr(), na._lib.F32, n, True, od.data_ptr(), bound)
+                dec.wait()
+
+            for _ in range(3):
+                one()
+            ms, _ = timed(one, max(3, K // 2))
+            ms /= max(3, K // 2)
+            dec.set_profiling(True)
+            one()
+            km = dict(dec.kernel_times_ms())
+            dec.set_profiling(False)
+            nw = dec.last_counts()["n_work"]
+        host_out = np.zeros(bound, dtype=np.float32)
+        nout = C.c_uint64(0)
+        cb0 = na._lib.STATUS_CB()
+
+        def call():
+            rc = lib.apt_decode(x.ctypes.data, n, rate, C.byref(cset), 1, host_out.ctypes.data, bound, C.byref(nout), cb0, None)
+            if rc != 0:
+                raise SystemExit(f"apt_decode({rate} Hz) failed: {rc}")
+
+        call()
+        ems, _ = timed(call, 3)
+        ems /= 3
+        lib.apt_cache_clear()
+        peak, _ = measured_peaks()
+        k_ms = km.get("resample_envelope")
+        out[str(rate)] = {"value": n / (ms * 1e-3) / 1e6, "ms_per_decode": ms, "e2e_apt_decode_value": n / (ems * 1e-3) / 1e6,
+                          "e2e_ms": ems, "resample_envelope_ms": k_ms,
+                          "resample_envelope_frac_of_hbm_roofline": (4 * n + 4 * nw) / (k_ms * 1e-3) / 1e9 / peak if k_ms else None,
+                          "kernels_ms": km}
+    return out
 
 
 def main():

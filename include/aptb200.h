@@ -149,6 +149,10 @@ int apt_decode_len_bound(uint64_t n, uint32_t input_rate, const apt_settings *s,
 int apt_decode(const float *signal, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
                float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user);
 
+/* apt_decode / apt_decode_pcm16 keep the decoder they used (plan, device workspaces, pinned staging) parked per
+ * (device, rate, settings) for the next call; this frees the parked ones.  Thread-safe. */
+void apt_cache_clear(void);
+
 /* Same, taking the PCM16 samples of the WAV directly: the `as f32` cast of wav::load_wav
  * (wav.rs:31-40) is fused into the resampler's load, halving the host->device bytes. */
 int apt_decode_pcm16(const int16_t *pcm, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
@@ -176,6 +180,8 @@ int apt_decoder_submit_device(apt_decoder *dec, const void *signal, int format, 
                               float *out, uint64_t cap);
 int apt_decoder_submit_host(apt_decoder *dec, const void *signal, int format, uint64_t n, int sync,
                             float *out, uint64_t cap);
+/* 1 if the decoder's job has finished (apt_decoder_wait will not block) or none is in flight, else 0. */
+int apt_decoder_poll(apt_decoder *dec);
 /* Block until the job is finished; returns its status (APT_ERR_FEW_SYNC_FRAMES etc.) and *nout. */
 int apt_decoder_wait(apt_decoder *dec, uint64_t *nout);
 
@@ -184,6 +190,9 @@ int apt_decoder_last_sync(apt_decoder *dec, uint64_t *positions, size_t cap, siz
 int apt_decoder_last_counts(apt_decoder *dec, uint64_t *n_work, uint64_t *n_rows, uint64_t *n_peaks);
 /* Number of "roots" of the sync correlation the peak picker worked on in the last job (diagnostic). */
 int apt_decoder_last_root_count(apt_decoder *dec, uint64_t *n_roots);
+/* The roots themselves, ascending (a root is a correlation index p with no larger value in (p, p + min_distance]: the
+ * only places a sync position can land -- DESIGN.md "Peak picker").  Diagnostic; valid after a wait() of a sync job. */
+int apt_decoder_last_roots(apt_decoder *dec, uint64_t *roots, size_t cap, size_t *nroots);
 /* Copy an intermediate signal of the last job back to the host (what Context::step would dump):
  * which = 0 "demodulation_result" input i.e. resample+envelope output, 1 "filter_result",
  * 2 "sync_correlation". */
@@ -200,6 +209,11 @@ int apt_decoder_kernel_ms(apt_decoder *dec, float *ms, int cap, int *count);
 void *apt_decoder_stream(apt_decoder *dec);
 /* Kernel launches issued by this decoder since creation. */
 uint64_t apt_decoder_launch_count(apt_decoder *dec);
+
+/* Binds the calling thread to the CPUs of the NUMA node CUDA device `device` hangs off (sysfs local_cpulist), so that
+ * pinned buffers it allocates afterwards and its copy loops are local to the GPU's PCIe root.  1 if bound, 0 if the
+ * topology is unknown / APTB200_NO_AFFINITY is set.  The library binds its own feeder and copy threads this way. */
+int apt_bind_thread_to_device(int device);
 
 /* Pinned host memory for asynchronous submit_host (cudaHostAlloc / cudaFreeHost). */
 int apt_host_alloc(void **ptr, size_t bytes);
@@ -245,7 +259,8 @@ int apt_ut_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_ut_
 /* ------------------------------------------------------------------ batch */
 
 /* Decode `count` independent recordings (all at `input_rate`, same settings), sharded
- * recording i -> device devices[i % ndevices], streams_per_device jobs in flight per device,
+ * recording i -> device devices[i % ndevices]; one feeder thread per device (bound to the device's NUMA node)
+ * keeps streams_per_device jobs in flight and takes them back in completion order;
  * no inter-device communication.  signals[i]/lens[i] are host buffers; outs[i] (capacity caps[i]
  * floats) receive the rows, nouts[i] the counts and statuses[i] the per-recording status.
  * Returns APT_OK if every recording decoded, else the first failing status. */

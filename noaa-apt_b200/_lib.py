@@ -91,10 +91,14 @@ SIGNATURES = {
     "apt_decoder_destroy": (None, [C.c_void_p]),
     "apt_decoder_submit_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64]),
     "apt_decoder_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64]),
+    "apt_decoder_poll": (C.c_int, [C.c_void_p]),
+    "apt_cache_clear": (None, []),
+    "apt_bind_thread_to_device": (C.c_int, [C.c_int]),
     "apt_decoder_wait": (C.c_int, [C.c_void_p, _u64p]),
     "apt_decoder_last_sync": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, _szp]),
     "apt_decoder_last_counts": (C.c_int, [C.c_void_p, _u64p, _u64p, _u64p]),
     "apt_decoder_last_root_count": (C.c_int, [C.c_void_p, _u64p]),
+    "apt_decoder_last_roots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, _szp]),
     "apt_decoder_read_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, _u64p]),
     "apt_decoder_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "apt_decoder_kernel_count": (C.c_int, [C.c_void_p]),

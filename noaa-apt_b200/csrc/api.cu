@@ -4,6 +4,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "aptb200.h"
@@ -18,6 +21,9 @@ namespace aptb200 {
 int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int sync, float *rows_out,
                     const void *host_chunked);
 int run_find_sync(apt_decoder *d, uint64_t nwork);
+int ensure_legacy_sync(apt_decoder *d);
+int redo_sync_legacy(apt_decoder *d);
+int materialise_stages(apt_decoder *d);
 }  // namespace aptb200
 
 namespace {
@@ -54,9 +60,12 @@ int free_decoder_buffers(apt_decoder *d) {
     if (d->stream) cudaStreamSynchronize(d->stream);
     for (void *p : {(void *)d->d_h, (void *)d->d_lp, (void *)d->d_one, (void *)d->d_guard, d->d_in, (void *)d->d_r,
                     (void *)d->d_e, (void *)d->d_f, (void *)d->d_corr, (void *)d->d_aligned, (void *)d->d_root_list,
-                    (void *)d->d_root_count, (void *)d->d_pos, (void *)d->d_res, (void *)d->d_out, d->d_pick, (void *)d->d_tile_taps, (void *)d->d_tile_xs, (void *)d->d_conv})
+                    (void *)d->d_root_count, (void *)d->d_pos, (void *)d->d_res, (void *)d->d_out, d->d_pick, (void *)d->d_tile_taps, (void *)d->d_tile_xs, (void *)d->d_conv,
+                    (void *)d->d_ctl, (void *)d->d_desc, (void *)d->d_pool, (void *)d->d_roots2, (void *)d->d_tile_base, (void *)d->d_by_id})
         if (p) cudaFree(p);
     if (d->h_res) cudaFreeHost(d->h_res);
+    if (d->h_out) cudaFreeHost(d->h_out);
+    d->own_stager.reset();
     for (auto e : d->ev_begin) cudaEventDestroy(e);
     for (auto e : d->ev_end) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
@@ -68,27 +77,46 @@ int free_decoder_buffers(apt_decoder *d) {
     return APT_OK;
 }
 
-// Allocates what find_sync needs for up to max_work work-rate samples.
+// Allocates what find_sync needs for up to max_work work-rate samples: the picker's buffers always, the fused stage's
+// record pool when the plan has one (the legacy f / corr / per-block root lists come on first use: ensure_legacy_sync).
 int alloc_sync_buffers(apt_decoder *d) {
     const Plan &p = d->plan;
+    if (getenv("APTB200_SEQUENTIAL_PICK")) d->use_parallel_pick = false;
+    if (getenv("APTB200_GENERIC_LOWPASS")) d->use_fused_lowpass = false;
     if (!p.work_multiple || d->max_work <= p.guard.size()) return APT_OK;
+    if (p.dist > 16384) return APT_OK;   // k_roots holds two blocks of min_distance floats in shared memory (work_rate <=
+                                         // 9 * 4160): decoding with sync is refused at submit, --no-sync still works
     d->max_corr = d->max_work - p.guard.size();
     d->max_blocks = static_cast<uint32_t>((d->max_corr + p.dist - 1) / p.dist);
     d->max_positions = static_cast<uint32_t>(d->max_work / p.row + 4);
+    d->use_records = d->use_fused_lowpass && !getenv("APTB200_LEGACY_SYNC") &&
+                     lowpass_corr_supported(static_cast<u32>(p.lp.size()), p.dec);
+    if (d->use_records) {
+        d->tile_w = records_tile(p.dec);
+        d->max_tiles = static_cast<uint32_t>((d->max_corr + d->tile_w - 1) / d->tile_w);
+        uint64_t cap = std::max<uint64_t>(d->max_corr / 2, 1u << 16);
+        if (const char *e = getenv("APTB200_RECORD_POOL")) cap = std::max<uint64_t>(strtoull(e, nullptr, 10), 64);
+        d->pool_cap = static_cast<uint32_t>(std::min<uint64_t>(cap, 1u << 30));
+        APT_CUDA(cudaMalloc(&d->d_ctl, sizeof(SyncCtl)));
+        APT_CUDA(cudaMemset(d->d_ctl, 0, sizeof(SyncCtl)));
+        APT_CUDA(cudaMalloc(&d->d_desc, static_cast<size_t>(d->max_tiles) * sizeof(TileDesc)));
+        APT_CUDA(cudaMalloc(&d->d_pool, static_cast<size_t>(d->pool_cap) * sizeof(Rec)));
+        APT_CUDA(cudaMalloc(&d->d_roots2, static_cast<size_t>(d->pool_cap) * sizeof(u32)));
+        APT_CUDA(cudaMalloc(&d->d_by_id, static_cast<size_t>(d->pool_cap) * sizeof(u32)));
+        APT_CUDA(cudaMalloc(&d->d_tile_base, static_cast<size_t>(d->max_tiles) * sizeof(u32)));
+    }
+    const uint32_t count_blocks = std::max(d->max_blocks, d->max_tiles);
     APT_CUDA(cudaMalloc(&d->d_guard, p.guard.size()));
     APT_CUDA(cudaMemcpy(d->d_guard, p.guard.data(), p.guard.size(), cudaMemcpyHostToDevice));
-    APT_CUDA(cudaMalloc(&d->d_corr, d->max_corr * sizeof(float)));
-    APT_CUDA(cudaMalloc(&d->d_root_list, static_cast<size_t>(d->max_blocks) * p.dist * sizeof(u32)));
-    APT_CUDA(cudaMalloc(&d->d_root_count, static_cast<size_t>(d->max_blocks) * sizeof(u32)));
+    APT_CUDA(cudaMalloc(&d->d_root_count, static_cast<size_t>(count_blocks) * sizeof(u32)));
     APT_CUDA(cudaMalloc(&d->d_pos, static_cast<size_t>(d->max_positions) * sizeof(u32)));
     // parallel picker: room for every row-aligned start plus ~63 roots per row (noisy recordings have ~35);
     // beyond that the kernel falls back to the sequential walk by itself.
     const u32 cap = static_cast<u32>(std::min<uint64_t>(static_cast<uint64_t>(d->max_positions) * 64 + 65536, 1u << 28));
-    APT_CUDA(cudaMalloc(&d->d_pick, pick_scratch_bytes(d->max_blocks, d->max_positions, cap)));
-    d->pick = pick_scratch_carve(d->d_pick, d->max_blocks, d->max_positions, cap);
+    APT_CUDA(cudaMalloc(&d->d_pick, pick_scratch_bytes(count_blocks, d->max_positions, cap)));
+    d->pick = pick_scratch_carve(d->d_pick, count_blocks, d->max_positions, cap);
     APT_CUDA(cudaMemset(d->pick.ticket, 0, 8));
-    if (getenv("APTB200_SEQUENTIAL_PICK")) d->use_parallel_pick = false;
-    if (getenv("APTB200_GENERIC_LOWPASS")) d->use_fused_lowpass = false;
+    if (d->d_ctl) d->pick.ticket = &d->d_ctl->pad[0];   // zeroed with the control block at the start of every job
     return APT_OK;
 }
 
@@ -348,8 +376,9 @@ extern "C" int apt_find_sync(const float *signal, uint64_t n, uint32_t work_rate
         *npositions = 1;
         return APT_OK;
     }
+    d.use_fused_lowpass = false;            // the stage entry point takes an already filtered signal: exact-order kernels
     APT_TRY(alloc_sync_buffers(&d));
-    APT_CUDA(cudaMalloc(&d.d_f, n * sizeof(float)));
+    APT_TRY(ensure_legacy_sync(&d));
     APT_CUDA(cudaMalloc(&d.d_res, sizeof(SyncResult)));
     APT_CUDA(cudaMemsetAsync(d.d_res, 0, sizeof(SyncResult), d.stream));
     APT_CUDA(cudaMemcpyAsync(d.d_f, signal, n * sizeof(float), cudaMemcpyHostToDevice, d.stream));
@@ -408,6 +437,7 @@ extern "C" int apt_decoder_create(int device, uint32_t input_rate, const apt_set
         // staging for host submits: whole recording up to 64 Mi samples, else two chunks of 32 Mi (APTB200_CHUNK_SAMPLES overrides)
         uint64_t chunk = 32ull << 20;
         if (const char *e = getenv("APTB200_CHUNK_SAMPLES")) chunk = std::max<uint64_t>(strtoull(e, nullptr, 10), 1u << 16);
+        chunk &= ~7ull;   // both staging halves stay 16-byte aligned for f32 and PCM16 samples
         d->chunk_samples = (max_samples > 2 * chunk && p.first_polyphase) ? chunk : 0;
         if (getenv("APTB200_CHUNK_SAMPLES") && max_samples > chunk && p.first_polyphase) d->chunk_samples = chunk;
     }
@@ -433,8 +463,8 @@ extern "C" int apt_decoder_create(int device, uint32_t input_rate, const apt_set
     const size_t work_bytes = std::max<uint64_t>(d->max_work, 1) * sizeof(float);
     if (!p.first_polyphase) APT_CUDA(cudaMalloc(&d->d_r, work_bytes));
     APT_CUDA(cudaMalloc(&d->d_e, work_bytes));
-    APT_CUDA(cudaMalloc(&d->d_f, work_bytes));
     APT_TRY(alloc_sync_buffers(d.get()));
+    if (!d->use_records) APT_TRY(ensure_legacy_sync(d.get()));
     APT_CUDA(cudaMalloc(&d->d_res, sizeof(SyncResult)));
     APT_CUDA(cudaMemset(d->d_res, 0, sizeof(SyncResult)));
     APT_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&d->h_res), sizeof(SyncResult), cudaHostAllocDefault));
@@ -478,13 +508,29 @@ int submit_common(apt_decoder *d, const void *signal, int format, uint64_t n, in
         d->job_status = fail(APT_ERR_TOO_SHORT, "Got less than 10 rows of samples, audio file is too short");
         return d->job_status;
     }
+    if (d->job_sync && p.work_multiple && !d->d_pos)
+        return fail(APT_ERR_BAD_ARG, "work_rate %u is too high for the sync picker (min_distance %u > 16384); decode without "
+                                     "sync or use a work_rate <= 37440", p.st.work_rate, p.dist);
     const uint64_t need = d->job_sync ? (nwork / p.row) * kPxPerRow : plan_out_bound(p, n);
     if (!out || cap < need) return fail(APT_ERR_CAPACITY, "output needs room for %llu floats", (unsigned long long)need);
 
     const void *dev_in = signal;
     float *rows_dst = out;
     const void *host_chunked = nullptr;
+    d->job_in_pageable = d->job_out_pageable = false;
     if (host) {
+        d->job_in_pageable = is_pageable(signal);
+        d->job_out_pageable = is_pageable(out);
+        if ((d->job_in_pageable || d->job_out_pageable) && !d->stager && !getenv("APTB200_NO_STAGER")) {
+            int threads = 8;
+            if (const char *e = getenv("APTB200_COPY_THREADS")) threads = std::max(1, atoi(e));
+            d->own_stager.reset(new (std::nothrow) HostStager(d->device, 16u << 20, 3, threads));
+            if (d->own_stager && !d->own_stager->ok()) d->own_stager.reset();
+            d->stager = d->own_stager.get();
+        }
+        if (d->job_out_pageable && !d->h_out)
+            APT_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&d->h_out), std::max<uint64_t>(d->max_out, 1) * sizeof(float),
+                                   cudaHostAllocDefault));
         // Recordings longer than the chunk size are uploaded in chunks that overlap the resampling; shorter ones
         // (and the L == 1 first stage) are staged whole.
         const bool chunked = d->chunk_samples != 0 && n > d->chunk_samples && p.first_polyphase;
@@ -510,6 +556,9 @@ int submit_common(apt_decoder *d, const void *signal, int format, uint64_t n, in
             }
             host_chunked = signal;
             dev_in = nullptr;
+        } else if (d->job_in_pageable && d->stager) {
+            APT_CUDA(d->stager->upload(d->d_in, signal, n * sample_bytes(format), d->stream));
+            dev_in = d->d_in;
         } else {
             APT_CUDA(cudaMemcpyAsync(d->d_in, signal, n * sample_bytes(format), cudaMemcpyHostToDevice, d->stream));
             dev_in = d->d_in;
@@ -523,10 +572,16 @@ int submit_common(apt_decoder *d, const void *signal, int format, uint64_t n, in
         d->job_status = st;
         return st;
     }
-    if (d->job_sync)
-        APT_CUDA(cudaMemcpyAsync(d->h_res, d->d_res, sizeof(SyncResult), cudaMemcpyDeviceToHost, d->stream));
-    else if (host && d->job_fixed_out)
-        APT_CUDA(cudaMemcpyAsync(out, d->d_out, d->job_fixed_out * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+    if (d->job_sync) APT_CUDA(cudaMemcpyAsync(d->h_res, d->d_res, sizeof(SyncResult), cudaMemcpyDeviceToHost, d->stream));
+    d->job_d2h_floats = 0;
+    if (host) {
+        // the rows come back with the job: when syncing n_rows is only known on the device, so the copy covers the bound
+        // (at most one row more than is produced)
+        d->job_d2h_floats = d->job_sync ? need : d->job_fixed_out;
+        if (d->job_d2h_floats)
+            APT_CUDA(cudaMemcpyAsync(d->job_out_pageable ? d->h_out : out, d->d_out, d->job_d2h_floats * sizeof(float),
+                                     cudaMemcpyDeviceToHost, d->stream));
+    }
     d->in_flight = true;
     return APT_OK;
 }
@@ -553,7 +608,19 @@ extern "C" int apt_decoder_wait(apt_decoder *d, uint64_t *nout) {
     uint64_t produced = d->job_fixed_out;
     d->last_work = d->job_work;
     d->last_peaks = 0;
+    d->last_fused = d->job_fused;
     if (d->job_sync) {
+        if (d->h_res->status == kSyncRedo) {
+            // the record pool of the fused stage overflowed (silence, ramps: every index a record): the sync stage runs
+            // again with the legacy kernels on the envelope that is still in d_e
+            APT_TRY(redo_sync_legacy(d));
+            APT_CUDA(cudaMemcpyAsync(d->h_res, d->d_res, sizeof(SyncResult), cudaMemcpyDeviceToHost, d->stream));
+            if (d->job_host && d->job_d2h_floats)
+                APT_CUDA(cudaMemcpyAsync(d->job_out_pageable ? d->h_out : d->job_out, d->d_out, d->job_d2h_floats * sizeof(float),
+                                         cudaMemcpyDeviceToHost, d->stream));
+            APT_CUDA(cudaStreamSynchronize(d->stream));
+            d->last_fused = false;
+        }
         const SyncResult res = *d->h_res;
         d->last_peaks = res.n_peaks;
         if (res.status != APT_OK) {
@@ -562,10 +629,10 @@ extern "C" int apt_decoder_wait(apt_decoder *d, uint64_t *nout) {
             return d->job_status;
         }
         produced = static_cast<uint64_t>(res.n_rows) * kPxPerRow;
-        if (d->job_host && produced) {
-            APT_CUDA(cudaMemcpyAsync(d->job_out, d->d_out, produced * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
-            APT_CUDA(cudaStreamSynchronize(d->stream));
-        }
+    }
+    if (d->job_host && d->job_out_pageable && produced) {
+        if (d->stager) d->stager->scatter(d->job_out, d->h_out, produced * sizeof(float));
+        else memcpy(d->job_out, d->h_out, produced * sizeof(float));
     }
     d->last_rows = d->plan.work_multiple ? produced / kPxPerRow : 0;
     d->last_out = produced;
@@ -604,11 +671,44 @@ extern "C" int apt_decoder_last_root_count(apt_decoder *d, uint64_t *n_roots) {
     return APT_OK;
 }
 
+extern "C" int apt_decoder_last_roots(apt_decoder *d, uint64_t *roots, size_t cap, size_t *nroots) {
+    if (!d || !nroots) return fail(APT_ERR_BAD_ARG, "null argument");
+    *nroots = 0;
+    if (!d->d_root_count || d->last_work <= d->plan.guard.size()) return APT_OK;
+    APT_CUDA(cudaSetDevice(d->device));
+    const uint64_t ncorr = d->last_work - d->plan.guard.size();
+    const bool fused = d->last_fused && d->d_desc;
+    const uint32_t block = fused ? d->tile_w : d->plan.dist;
+    const uint32_t nb = static_cast<uint32_t>((ncorr + block - 1) / block);
+    std::vector<u32> counts(nb);
+    APT_CUDA(cudaMemcpy(counts.data(), d->d_root_count, nb * sizeof(u32), cudaMemcpyDeviceToHost));
+    std::vector<TileDesc> desc;
+    if (fused) {
+        desc.resize(nb);
+        APT_CUDA(cudaMemcpy(desc.data(), d->d_desc, nb * sizeof(TileDesc), cudaMemcpyDeviceToHost));
+    }
+    size_t total = 0;
+    std::vector<u32> tmp;
+    for (uint32_t b = 0; b < nb; ++b) {
+        if (roots && counts[b]) {
+            tmp.resize(counts[b]);
+            const u32 *src = fused ? d->d_roots2 + desc[b].off : d->d_root_list + static_cast<size_t>(b) * block;
+            APT_CUDA(cudaMemcpy(tmp.data(), src, counts[b] * sizeof(u32), cudaMemcpyDeviceToHost));
+            for (u32 i = 0; i < counts[b]; ++i)
+                if (total + i < cap) roots[total + i] = tmp[i];
+        }
+        total += counts[b];
+    }
+    *nroots = total;
+    return APT_OK;
+}
+
 extern "C" int apt_decoder_read_stage(apt_decoder *d, int which, float *out, uint64_t cap, uint64_t *n) {
     if (!d || !n) return fail(APT_ERR_BAD_ARG, "null argument");
     APT_CUDA(cudaSetDevice(d->device));
     const float *src = nullptr;
     uint64_t len = d->last_work;
+    if (which != 0 && d->last_fused && len) APT_TRY(materialise_stages(d));   // f / corr were never written: compute them now
     switch (which) {
     case 0: src = d->d_e; break;
     case 1: src = d->d_f; break;
@@ -693,13 +793,67 @@ extern "C" int apt_memcpy_d2h(int device, void *dst, const void *src, size_t byt
 
 namespace {
 
+// apt_decode() is what the Rust shim binds (rust/decode.rs): one call per recording, ordinary pageable buffers.  Creating a
+// decoder costs ~14 cudaMalloc + a stream + pinned staging, so finished decoders are parked here, keyed by what their plan
+// depends on, and the next call with the same (device, rate, settings) takes one over.  apt_cache_clear() frees them.
+struct CacheEntry {
+    int device;
+    uint32_t rate;
+    apt_settings st;
+    apt_decoder *dec;
+    uint64_t stamp;
+};
+std::mutex g_cache_mutex;
+std::vector<CacheEntry> g_cache;
+uint64_t g_cache_stamp = 0;
+constexpr size_t kCacheMaxIdle = 8;
+
+bool same_settings(const apt_settings &a, const apt_settings &b) { return memcmp(&a, &b, sizeof(a)) == 0; }
+
+apt_decoder *cache_take(int device, uint32_t rate, const apt_settings &st, uint64_t n) {
+    std::lock_guard<std::mutex> lk(g_cache_mutex);
+    for (size_t i = 0; i < g_cache.size(); ++i) {
+        const CacheEntry &e = g_cache[i];
+        if (e.device == device && e.rate == rate && same_settings(e.st, st) && e.dec->max_samples >= n) {
+            apt_decoder *d = e.dec;
+            g_cache.erase(g_cache.begin() + static_cast<long>(i));
+            return d;
+        }
+    }
+    return nullptr;
+}
+
+void cache_put(int device, uint32_t rate, const apt_settings &st, apt_decoder *d) {
+    apt_decoder *victim = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mutex);
+        // one idle decoder per key is enough for a sequential caller: a smaller one of the same key is replaced
+        for (size_t i = 0; i < g_cache.size(); ++i) {
+            CacheEntry &e = g_cache[i];
+            if (e.device == device && e.rate == rate && same_settings(e.st, st) && e.dec->max_samples <= d->max_samples) {
+                victim = e.dec;
+                g_cache.erase(g_cache.begin() + static_cast<long>(i));
+                break;
+            }
+        }
+        if (!victim && g_cache.size() >= kCacheMaxIdle) {
+            size_t lru = 0;
+            for (size_t i = 1; i < g_cache.size(); ++i)
+                if (g_cache[i].stamp < g_cache[lru].stamp) lru = i;
+            victim = g_cache[lru].dec;
+            g_cache.erase(g_cache.begin() + static_cast<long>(lru));
+        }
+        g_cache.push_back(CacheEntry{device, rate, st, d, ++g_cache_stamp});
+    }
+    if (victim) apt_decoder_destroy(victim);
+}
+
 int decode_oneshot(const void *signal, int format, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
                    float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user) {
     if (!s || !nout) return fail(APT_ERR_BAD_ARG, "null argument");
     *nout = 0;
     if (n == 0 || !signal) return fail(APT_ERR_BAD_ARG, "empty signal");
     int device = 0;
-    apt_decoder *d = nullptr;
     {
         // errors that do not need a device come first, in the reference's order
         Plan p;
@@ -710,16 +864,39 @@ int decode_oneshot(const void *signal, int format, uint64_t n, uint32_t input_ra
     }
     APT_TRY(require_device());
     if (cudaGetDevice(&device) != cudaSuccess) device = 0;
-    APT_TRY(apt_decoder_create(device, input_rate, s, n, &d));
+    static const bool use_cache = getenv("APTB200_NO_CACHE") == nullptr;
+    apt_decoder *d = use_cache ? cache_take(device, input_rate, *s, n) : nullptr;
+    if (!d) {
+        // head-room so that the next, slightly longer recording of a series reuses the decoder
+        const uint64_t room = use_cache ? ((n + n / 8 + (1u << 20)) & ~((1ull << 20) - 1)) : n;
+        APT_TRY(apt_decoder_create(device, input_rate, s, room, &d));
+    }
     d->cb = cb;
     d->cb_user = user;
     int st = apt_decoder_submit_host(d, signal, format, n, sync, out, cap);
     if (st == APT_OK) st = apt_decoder_wait(d, nout);
-    apt_decoder_destroy(d);
+    d->cb = nullptr;
+    d->cb_user = nullptr;
+    if (use_cache) cache_put(device, input_rate, *s, d);
+    else apt_decoder_destroy(d);
     return st;
 }
 
 }  // namespace
+
+extern "C" int apt_bind_thread_to_device(int device) {
+    if (require_device() != APT_OK) return 0;
+    return bind_thread_to_device(device) ? 1 : 0;
+}
+
+extern "C" void apt_cache_clear(void) {
+    std::vector<CacheEntry> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mutex);
+        drop.swap(g_cache);
+    }
+    for (auto &e : drop) apt_decoder_destroy(e.dec);
+}
 
 extern "C" int apt_decode(const float *signal, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
                           float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user) {
@@ -771,6 +948,16 @@ extern "C" int apt_ut_plan(uint32_t l, uint32_t m, const float *taps, size_t nta
 
 // ===================================================================================== batch
 
+extern "C" int apt_decoder_poll(apt_decoder *d) {
+    if (!d || !d->in_flight) return 1;
+    cudaSetDevice(d->device);
+    const cudaError_t e = cudaStreamQuery(d->stream);
+    if (e == cudaErrorNotReady) return 0;
+    return 1;   // finished (or failed: wait() reports it)
+}
+
+// One feeder thread per device: binds itself to the device's NUMA node, owns `streams_per_device` decoders and one copy
+// stager, keeps every decoder busy and reaps the jobs in the order they complete.  Nothing is shared between devices.
 extern "C" int apt_decode_batch(const void *const *signals, int format, const uint64_t *lens, int count,
                                 uint32_t input_rate, const apt_settings *s, int sync, float *const *outs,
                                 const uint64_t *caps, uint64_t *nouts, int *statuses, const int *devices, int ndevices,
@@ -786,46 +973,102 @@ extern "C" int apt_decode_batch(const void *const *signals, int format, const ui
     }
     if (streams_per_device <= 0) streams_per_device = 4;
     uint64_t max_len = 0;
-    for (int i = 0; i < count; ++i) max_len = std::max(max_len, lens[i]);
-
-    const int nslots = ndevices * streams_per_device;   // decoders are created lazily
-    std::vector<apt_decoder *> slots(nslots, nullptr);
-    std::vector<int> slot_job(nslots, -1);
-    int first_error = APT_OK;
-    auto finish = [&](int slot) {
-        const int job = slot_job[slot];
-        if (job < 0) return;
-        uint64_t got = 0;
-        int st = apt_decoder_wait(slots[slot], &got);
-        nouts[job] = got;
-        if (statuses) statuses[job] = st;
-        if (st != APT_OK && first_error == APT_OK) first_error = st;
-        slot_job[slot] = -1;
-    };
-    int fatal = APT_OK;
-    for (int i = 0; i < count && fatal == APT_OK; ++i) {
-        // recording i -> device i % G, stream (i / G) % S   
-        const int dev_idx = i % ndevices;
-        const int slot = dev_idx * streams_per_device + (i / ndevices) % streams_per_device;
-        if (!slots[slot]) {
-            fatal = apt_decoder_create(devices[dev_idx], input_rate, s, max_len, &slots[slot]);
-            if (fatal != APT_OK) break;
-        }
-        finish(slot);
+    for (int i = 0; i < count; ++i) {
+        max_len = std::max(max_len, lens[i]);
         nouts[i] = 0;
-        int st = apt_decoder_submit_host(slots[slot], signals[i], format, lens[i], sync, outs[i], caps[i]);
-        if (st == APT_OK) {
-            slot_job[slot] = i;
-        } else {
-            if (statuses) statuses[i] = st;
-            if (first_error == APT_OK) first_error = st;
-        }
+        if (statuses) statuses[i] = APT_ERR_CUDA;      // overwritten by the job's own status; never left "ok" by default
     }
-    for (int slot = 0; slot < nslots; ++slot) {
-        if (slots[slot]) {
-            finish(slot);
-            apt_decoder_destroy(slots[slot]);
+    std::vector<int> local_status(count, APT_ERR_CUDA);
+    std::vector<std::string> messages(ndevices);
+    std::vector<int> fatal(ndevices, APT_OK);
+
+    auto feeder = [&](int g) {
+        const int device = devices[g];
+        bind_thread_to_device(device);
+        std::vector<apt_decoder *> decs;
+        std::vector<int> job_of;
+        std::unique_ptr<HostStager> stager;
+        int next = g;                                  // recording i -> device i % G   
+        int in_flight = 0;
+        auto reap = [&](size_t k) {
+            uint64_t got = 0;
+            const int st = apt_decoder_wait(decs[k], &got);
+            const int job = job_of[k];
+            nouts[job] = got;
+            local_status[job] = st;
+            job_of[k] = -1;
+            --in_flight;
+        };
+        auto fail_rest = [&](int st) {
+            fatal[g] = st;
+            messages[g] = apt_last_error();
+            for (; next < count; next += ndevices) local_status[next] = st;
+        };
+        while (next < count || in_flight > 0) {
+            // a free decoder takes the next recording of this device
+            size_t free_k = decs.size();
+            for (size_t k = 0; k < decs.size(); ++k)
+                if (job_of[k] < 0) { free_k = k; break; }
+            if (next < count && (free_k < decs.size() || static_cast<int>(decs.size()) < streams_per_device)) {
+                if (free_k == decs.size()) {
+                    apt_decoder *d = nullptr;
+                    const int st = apt_decoder_create(device, input_rate, s, max_len, &d);
+                    if (st != APT_OK) {
+                        if (decs.empty()) { fail_rest(st); continue; }
+                        streams_per_device = static_cast<int>(decs.size());   // out of memory: make do with what exists
+                        continue;
+                    }
+                    if (!stager) {
+                        int threads = 8;
+                        if (const char *e = getenv("APTB200_COPY_THREADS")) threads = std::max(1, atoi(e));
+                        stager.reset(new (std::nothrow) HostStager(device, 16u << 20, 3, threads));
+                        if (stager && !stager->ok()) stager.reset();
+                    }
+                    d->stager = stager.get();
+                    decs.push_back(d);
+                    job_of.push_back(-1);
+                }
+                const int job = next;
+                next += ndevices;
+                const int st = apt_decoder_submit_host(decs[free_k], signals[job], format, lens[job], sync, outs[job], caps[job]);
+                if (st == APT_OK) {
+                    job_of[free_k] = job;
+                    ++in_flight;
+                } else {
+                    local_status[job] = st;
+                }
+                continue;
+            }
+            // every decoder is busy (or nothing is left to submit): take whichever job has finished, else the oldest
+            bool reaped = false;
+            for (size_t k = 0; k < decs.size() && !reaped; ++k)
+                if (job_of[k] >= 0 && apt_decoder_poll(decs[k])) { reap(k); reaped = true; }
+            if (!reaped) {
+                size_t oldest = decs.size();
+                for (size_t k = 0; k < decs.size(); ++k)
+                    if (job_of[k] >= 0 && (oldest == decs.size() || job_of[k] < job_of[oldest])) oldest = k;
+                if (oldest < decs.size()) reap(oldest);
+            }
         }
+        for (auto *d : decs) {
+            d->stager = nullptr;
+            apt_decoder_destroy(d);
+        }
+    };
+
+    if (ndevices == 1) {
+        feeder(0);
+    } else {
+        std::vector<std::thread> threads;
+        for (int g = 0; g < ndevices; ++g) threads.emplace_back(feeder, g);
+        for (auto &t : threads) t.join();
     }
-    return fatal != APT_OK ? fatal : first_error;
+    int first_error = APT_OK;
+    for (int i = 0; i < count; ++i) {
+        if (statuses) statuses[i] = local_status[i];
+        if (local_status[i] != APT_OK && first_error == APT_OK) first_error = local_status[i];
+    }
+    for (int g = 0; g < ndevices; ++g)
+        if (fatal[g] != APT_OK) return fail(fatal[g], "device %d: %s", devices[g], messages[g].c_str());
+    return first_error;
 }

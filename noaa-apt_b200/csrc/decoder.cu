@@ -69,6 +69,8 @@ int make_plan(uint32_t input_rate, const apt_settings &s, Plan &p) {
     p.sinphi = std::sin(phi);
 
     p.row = kPxPerRow * s.work_rate / kFinalRate;                       // decode.rs:55
+    if (p.row == 0)   // work_rate < 2: the reference divides by zero (decode.rs:141); a status is the safe equivalent
+        return fail(APT_ERR_BAD_ARG, "work_rate %u is too low: zero samples per image row", s.work_rate);
     p.dist = static_cast<uint32_t>(static_cast<uint64_t>(p.row) * 8 / 10);   // decode.rs:216
     p.work_multiple = s.work_rate % kFinalRate == 0;
     p.dec = s.work_rate / kFinalRate;
@@ -139,9 +141,69 @@ int run_find_sync(apt_decoder *d, uint64_t nwork) {
     }
     {
         Prof pr(d, "sync_pick");
-        APT_TRY(launch_pick(c, ncorr, nwork, p.row, p.dist, d->d_root_list, d->d_root_count, nblocks, d->d_pos,
-                            d->max_positions, d->d_res, d->use_parallel_pick && d->d_pick ? &d->pick : nullptr));
+        const u32 *boff = d->d_pick ? d->pick.block_off : nullptr;
+        const RootIndex ri{d->d_root_list, d->d_root_count, boff, nullptr, nullptr, boff ? boff + nblocks : nullptr, p.dist, nblocks};
+        APT_TRY(launch_pick(c, ncorr, nwork, p.row, p.dist, ri, d->d_pos, d->max_positions, d->d_res,
+                            d->use_parallel_pick && d->d_pick ? &d->pick : nullptr));
     }
+    return APT_OK;
+}
+
+// Legacy / debug buffers (f, corr, per-block root lists): generic shapes, read_stage, and the redo after a record-pool
+// overflow.  Allocated on first use.
+int ensure_legacy_sync(apt_decoder *d) {
+    const Plan &p = d->plan;
+    APT_CUDA(cudaSetDevice(d->device));
+    const size_t work_bytes = std::max<uint64_t>(d->max_work, 1) * sizeof(float);
+    if (!d->d_f) APT_CUDA(cudaMalloc(&d->d_f, work_bytes));
+    if (p.work_multiple && d->max_corr) {
+        if (!d->d_corr) APT_CUDA(cudaMalloc(&d->d_corr, d->max_corr * sizeof(float)));
+        if (!d->d_root_list) APT_CUDA(cudaMalloc(&d->d_root_list, static_cast<size_t>(d->max_blocks) * p.dist * sizeof(u32)));
+    }
+    return APT_OK;
+}
+
+// The back half with f and corr materialised in HBM: low-pass (+ correlation), roots, orbit walk, row gather.
+static int enqueue_back_legacy(apt_decoder *d, uint64_t nwork, int sync, float *rows_out) {
+    const Plan &p = d->plan;
+    const LaunchCtx c{d->stream, d->sm_count};
+    APT_TRY(ensure_legacy_sync(d));
+    d->job_corr_done = false;
+    const bool want_corr = sync && p.work_multiple && d->d_corr != nullptr;
+    const u32 ntaps = static_cast<u32>(p.lp.size());
+    if (d->use_fused_lowpass && lowpass_corr_supported(ntaps, p.dec) && p.work_multiple) {
+        // low-pass and (when syncing) the sync cross-correlation in one pass over the envelope
+        Prof pr(d, want_corr ? "lowpass_correlation" : "lowpass");
+        APT_TRY(launch_lowpass_corr(c, d->d_e, nwork, p.lp.data(), ntaps, p.dec, d->d_f, want_corr ? d->d_corr : nullptr));
+        d->job_corr_done = want_corr;
+    } else {
+        Prof pr(d, "lowpass");
+        APT_TRY(launch_fir_decimate(c, d->d_e, APT_F32, d->d_lp, ntaps, 1, nwork, d->d_f));
+    }
+    if (sync) {
+        APT_TRY(run_find_sync(d, nwork));
+        Prof pr(d, "gather_rows");
+        const u32 max_rows = static_cast<u32>(std::min<uint64_t>(nwork / p.row + 1, 1u << 30));
+        APT_TRY(launch_gather(c, d->d_f, d->d_pos, d->d_res, 0, max_rows, p.row, kPxPerRow, p.dec, rows_out));
+    }
+    return APT_OK;
+}
+
+// Re-runs the sync stage of the job that just drained with the legacy kernels (record pool overflow); d_e is intact.
+int redo_sync_legacy(apt_decoder *d) {
+    APT_CUDA(cudaMemsetAsync(d->d_res, 0, sizeof(SyncResult), d->stream));
+    return enqueue_back_legacy(d, d->job_work, 1, const_cast<float *>(d->job_rows_src));
+}
+
+// On-demand f / corr of the last job for read_stage after a fused run.
+int materialise_stages(apt_decoder *d) {
+    const Plan &p = d->plan;
+    const LaunchCtx c{d->stream, d->sm_count};
+    APT_TRY(ensure_legacy_sync(d));
+    const u32 ntaps = static_cast<u32>(p.lp.size());
+    APT_TRY(launch_lowpass_corr(c, d->d_e, d->last_work, p.lp.data(), ntaps, p.dec, d->d_f, d->d_corr));
+    APT_CUDA(cudaStreamSynchronize(d->stream));
+    d->last_fused = false;
     return APT_OK;
 }
 
@@ -224,8 +286,11 @@ static int enqueue_front_chunked(apt_decoder *d, const void *host, int format, u
                                                    (unsigned long long)xa, (unsigned long long)xb, (unsigned long long)cap);
         // copy stream: wait until the compute stream has finished with this buffer, then upload
         if (chunk >= 2) APT_CUDA(cudaStreamWaitEvent(d->copy_stream, d->ev_free[b], 0));
-        APT_CUDA(cudaMemcpyAsync(stage[b], static_cast<const char *>(host) + xa * sb, (xb - xa) * sb, cudaMemcpyHostToDevice,
-                                 d->copy_stream));
+        if (d->job_in_pageable && d->stager)
+            APT_CUDA(d->stager->upload(stage[b], static_cast<const char *>(host) + xa * sb, (xb - xa) * sb, d->copy_stream));
+        else
+            APT_CUDA(cudaMemcpyAsync(stage[b], static_cast<const char *>(host) + xa * sb, (xb - xa) * sb, cudaMemcpyHostToDevice,
+                                     d->copy_stream));
         APT_CUDA(cudaEventRecord(d->ev_copied[b], d->copy_stream));
         APT_CUDA(cudaStreamWaitEvent(d->stream, d->ev_copied[b], 0));
         // compute stream: (cast,) resample + envelope of this chunk's outputs
@@ -245,8 +310,7 @@ static int enqueue_front_chunked(apt_decoder *d, const void *host, int format, u
     return APT_OK;
 }
 
-static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n, uint64_t nwork, bool want_corr,
-                         const void *host_chunked) {
+static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n, uint64_t nwork, const void *host_chunked) {
     const Plan &p = d->plan;
     const LaunchCtx c{d->stream, d->sm_count};
     if (d->cb) {
@@ -288,17 +352,6 @@ static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n,
         APT_TRY(launch_envelope(c, d->d_r, nwork, p.cosphi2, p.sinphi, d->d_e));
     }
     if (d->cb) d->cb(0.42f, "Filtering", d->cb_user);                       // decode.rs:93
-    d->job_corr_done = false;
-    const u32 ntaps = static_cast<u32>(p.lp.size());
-    if (d->use_fused_lowpass && lowpass_corr_supported(ntaps, p.dec) && p.work_multiple) {
-        // low-pass and (when syncing) the sync cross-correlation in one pass over the envelope
-        Prof pr(d, want_corr ? "lowpass_correlation" : "lowpass");
-        APT_TRY(launch_lowpass_corr(c, d->d_e, nwork, p.lp.data(), ntaps, p.dec, d->d_f, want_corr ? d->d_corr : nullptr));
-        d->job_corr_done = want_corr;
-    } else {
-        Prof pr(d, "lowpass");
-        APT_TRY(launch_fir_decimate(c, d->d_e, APT_F32, d->d_lp, ntaps, 1, nwork, d->d_f));
-    }
     return APT_OK;
 }
 
@@ -311,18 +364,50 @@ int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int 
     d->job_work = nwork;
     d->ev_used = 0;
 
-    APT_TRY(enqueue_front(d, in, format, n, nwork, sync && p.work_multiple && d->d_corr != nullptr, host_chunked));
+    if (sync && d->use_records && d->d_ctl) APT_CUDA(cudaMemsetAsync(d->d_ctl, 0, sizeof(SyncCtl), d->stream));
+    APT_TRY(enqueue_front(d, in, format, n, nwork, host_chunked));
+    d->job_fused = false;
+    const u32 ntaps = static_cast<u32>(p.lp.size());
 
     if (sync) {
-        if (d->cb) d->cb(0.5f, "Syncing", d->cb_user);                      // decode.rs:107
-        if (!p.work_multiple)
+        if (!p.work_multiple) {
+            if (d->cb) d->cb(0.5f, "Syncing", d->cb_user);                  // decode.rs:107
             return fail(APT_ERR_WORK_RATE, "work_rate is not multiple of FINAL_RATE");   // decode.rs:172-176
-        APT_TRY(run_find_sync(d, nwork));
-        if (d->cb) d->cb(0.9f, "Resampling to 4160", d->cb_user);           // decode.rs:154
-        Prof pr(d, "gather_rows");
-        const u32 max_rows = static_cast<u32>(std::min<uint64_t>(nwork / p.row + 1, 1u << 30));
-        APT_TRY(launch_gather(c, d->d_f, d->d_pos, d->d_res, 0, max_rows, p.row, kPxPerRow, p.dec, rows_out));
+        }
         d->job_fixed_out = 0;
+        if (d->use_records && d->d_pool) {
+            // fused stage: f and corr stay on chip; records -> roots -> orbit -> rows straight from the envelope
+            const u64 ncorr = nwork - p.guard.size();
+            const u32 ntiles = static_cast<u32>((ncorr + d->tile_w - 1) / d->tile_w);
+            d->job_fused = true;
+            {
+                Prof pr(d, "lowpass_records");
+                APT_TRY(launch_lowpass_records(c, d->d_e, nwork, ncorr, p.lp.data(), ntaps, p.dec, d->d_ctl, d->d_desc, d->d_pool,
+                                               d->pool_cap, ntiles));
+            }
+            if (d->cb) d->cb(0.5f, "Syncing", d->cb_user);
+            {
+                Prof pr(d, "resolve_roots");
+                APT_TRY(launch_resolve_roots(c, d->d_desc, d->d_pool, ntiles, d->tile_w, p.dist, ncorr, d->d_roots2, d->d_root_count,
+                                             d->d_tile_base, d->d_by_id, d->d_ctl, d->d_res));
+            }
+            {
+                Prof pr(d, "sync_pick");
+                const RootIndex ri{d->d_roots2, d->d_root_count, d->d_tile_base, d->d_desc, d->d_by_id, &d->d_ctl->root_cursor,
+                                   d->tile_w, ntiles};
+                APT_TRY(launch_pick(c, ncorr, nwork, p.row, p.dist, ri, d->d_pos, d->max_positions, d->d_res,
+                                    d->use_parallel_pick && d->d_pick ? &d->pick : nullptr));
+            }
+            if (d->cb) d->cb(0.9f, "Resampling to 4160", d->cb_user);       // decode.rs:154
+            Prof pr(d, "gather_rows");
+            const u32 max_rows = static_cast<u32>(std::min<uint64_t>(nwork / p.row + 1, 1u << 30));
+            APT_TRY(launch_gather_lp(c, d->d_e, nwork, d->d_pos, d->d_res, 0, max_rows, p.row, kPxPerRow, p.dec, p.lp.data(), ntaps,
+                                     rows_out));
+            return APT_OK;
+        }
+        if (d->cb) d->cb(0.5f, "Syncing", d->cb_user);
+        APT_TRY(enqueue_back_legacy(d, nwork, 1, rows_out));
+        if (d->cb) d->cb(0.9f, "Resampling to 4160", d->cb_user);
         return APT_OK;
     }
 
@@ -330,12 +415,21 @@ int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int 
     const uint64_t rows = nwork / p.row;                                    // decode.rs:141-147
     if (d->cb) d->cb(0.9f, "Resampling to 4160", d->cb_user);
     if (p.work_multiple) {
-        Prof pr(d, "gather_rows");
-        APT_TRY(launch_gather(c, d->d_f, nullptr, d->d_res, static_cast<u32>(rows), static_cast<u32>(rows), p.row,
-                              kPxPerRow, p.dec, rows_out));
+        if (d->use_records) {
+            d->job_fused = true;
+            Prof pr(d, "gather_rows");
+            APT_TRY(launch_gather_lp(c, d->d_e, nwork, nullptr, d->d_res, static_cast<u32>(rows), static_cast<u32>(rows), p.row,
+                                     kPxPerRow, p.dec, p.lp.data(), ntaps, rows_out));
+        } else {
+            APT_TRY(enqueue_back_legacy(d, nwork, 0, rows_out));
+            Prof pr(d, "gather_rows");
+            APT_TRY(launch_gather(c, d->d_f, nullptr, d->d_res, static_cast<u32>(rows), static_cast<u32>(rows), p.row,
+                                  kPxPerRow, p.dec, rows_out));
+        }
         d->job_fixed_out = rows * kPxPerRow;
         return APT_OK;
     }
+    APT_TRY(enqueue_back_legacy(d, nwork, 0, rows_out));
     // work_rate is not a multiple of 4160: the final stage is a real L/M resample with the one-tap
     // NoFilter (dsp.rs:79-98), i.e. zero-stuffing then keeping every M-th sample.
     if (p.last.l == 0) return fail(APT_ERR_RESAMPLE_TO_ZERO, "Can't resample to 0Hz");

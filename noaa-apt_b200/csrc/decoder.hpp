@@ -9,7 +9,10 @@
 #include <cuda_runtime.h>
 
 #include "aptb200.h"
+#include <memory>
+
 #include "filters_host.hpp"
+#include "hostpool.hpp"
 #include "launch.hpp"
 
 namespace aptb200 {
@@ -76,6 +79,17 @@ struct apt_decoder {
     uint64_t conv_cap = 0;         // samples d_conv holds
     float *d_r = nullptr;          // resampled signal, only for the L == 1 first stage
     float *d_e = nullptr;          // envelope           ("demodulation_result")
+    // fused sync stage (kernels_sync2.cuh): f and corr never reach HBM; per-tile records -> roots
+    bool use_records = false;      // the fused stage serves this plan (standard / fast / slow profiles)
+    aptb200::u32 tile_w = 0, max_tiles = 0, pool_cap = 0;
+    aptb200::SyncCtl *d_ctl = nullptr;
+    aptb200::TileDesc *d_desc = nullptr;
+    aptb200::Rec *d_pool = nullptr;
+    aptb200::u32 *d_roots2 = nullptr;   // roots of tile t at d_roots2 + d_desc[t].off
+    aptb200::u32 *d_tile_base = nullptr, *d_by_id = nullptr;   // dense root ids: first id of tile t, position by id
+    bool job_fused = false;        // the current job ran the fused stage (f / corr were not materialised)
+    bool last_fused = false;
+    // legacy / debug buffers, allocated on first use (generic shapes, read_stage, pool overflow)
     float *d_f = nullptr;          // low-passed         ("filter_result")
     float *d_corr = nullptr;       // sync correlation   ("sync_correlation")
     float *d_aligned = nullptr;    // only when work_rate is not a multiple of 4160 (no-sync)
@@ -87,6 +101,12 @@ struct apt_decoder {
     bool use_fused_lowpass = true;
     bool job_corr_done = false;    // the correlation of the current job was produced by the fused low-pass kernel
     float *d_out = nullptr;        // rows for submit_host
+    // pageable host buffers (what the reference-facing apt_decode receives) go through a pinned ring + copy threads
+    aptb200::HostStager *stager = nullptr;                 // the one in use (own_stager, or the batch feeder's)
+    std::unique_ptr<aptb200::HostStager> own_stager;
+    float *h_out = nullptr;        // pinned landing buffer for the rows when the caller's buffer is pageable
+    bool job_in_pageable = false, job_out_pageable = false;
+    uint64_t job_d2h_floats = 0;   // rows copied back by the job (an upper bound when syncing: n_rows is not known yet)
     aptb200::SyncResult *h_res = nullptr;   // pinned
 
     // job in flight
@@ -94,6 +114,7 @@ struct apt_decoder {
     bool job_host = false, job_sync = false;
     int job_status = APT_OK;
     uint64_t job_n = 0, job_work = 0, job_corr = 0, job_fixed_out = 0;
+    const void *job_dev_in = nullptr;   // device address sample 0 would have (for a redo of the sync stage)
     float *job_out = nullptr;      // caller's buffer (host or device)
     uint64_t job_cap = 0;
     const float *job_rows_src = nullptr;

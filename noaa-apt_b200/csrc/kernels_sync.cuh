@@ -15,6 +15,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "kernels_generic.cuh"
@@ -25,6 +26,7 @@ namespace aptb200 {
 constexpr u32 kNoSeed = 0xFFFFFFFFu;
 
 __device__ __forceinline__ bool last_cta_arrives(u32 *ticket);
+template <int THREADS>
 __device__ void scan_root_counts(const u32 *root_count, u32 nblocks, u32 *block_off);
 
 // ---------------------------------------------------------------------------------------------
@@ -192,27 +194,30 @@ k_roots(const float *__restrict__ corr, u64 ncorr, u32 dist, u32 *__restrict__ r
     if (blockIdx.x == 0 && tid == 0) result->seed_index = s_seed;
     // the last CTA to finish numbers the roots densely (exclusive scan of the per-block counts)
     if (ticket != nullptr && last_cta_arrives(ticket)) {
-        scan_root_counts(root_count, gridDim.x, block_off);
+        scan_root_counts<THREADS>(root_count, gridDim.x, block_off);
         if (tid == 0) ticket[1] = 0;           // arrival counter of k_pick_links' grid barriers
     }
 }
 
 // Smallest root >= s.  Binary search in the block of s, then the first root of the following
 // blocks (the last correlation index is always a root, so the search terminates).
-__device__ __forceinline__ u32 first_root(u32 s, u32 dist, const u32 *__restrict__ root_list,
-                                          const u32 *__restrict__ root_count, u32 nblocks) {
-    u32 b = s / dist;
+__device__ __forceinline__ const u32 *ri_list(const RootIndex &ri, u32 b) {
+    return ri.list + (ri.desc ? static_cast<u64>(ri.desc[b].off) : static_cast<u64>(b) * ri.block);
+}
+
+__device__ __forceinline__ u32 first_root(u32 s, const RootIndex &ri) {
+    u32 b = s / ri.block;
     {
-        const u32 *list = root_list + static_cast<u64>(b) * dist;
-        u32 lo = 0, hi = root_count[b];
+        const u32 *list = ri_list(ri, b);
+        u32 lo = 0, hi = ri.count[b];
         while (lo < hi) {
             const u32 mid = (lo + hi) >> 1;
             if (list[mid] < s) lo = mid + 1; else hi = mid;
         }
-        if (lo < root_count[b]) return list[lo];
+        if (lo < ri.count[b]) return list[lo];
     }
-    for (++b; b < nblocks; ++b)
-        if (root_count[b] > 0) return root_list[static_cast<u64>(b) * dist];
+    for (++b; b < ri.nblocks; ++b)
+        if (ri.count[b] > 0) return ri_list(ri, b)[0];
     return 0xFFFFFFFFu;   // unreachable for s < ncorr
 }
 
@@ -220,19 +225,18 @@ __device__ __forceinline__ u32 first_root(u32 s, u32 dist, const u32 *__restrict
 // Sequential orbit walk by one thread: O(rows * log) dependent loads.  The always-correct
 // fallback (pathological inputs with millions of roots, e.g. silence) and the v0 picker.
 // ---------------------------------------------------------------------------------------------
-__device__ void pick_sequential(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ root_list,
-                                const u32 *__restrict__ root_count, u32 nblocks, u32 *__restrict__ positions,
+__device__ void pick_sequential(u64 ncorr, u64 nwork, u32 row, u32 dist, const RootIndex &ri, u32 *__restrict__ positions,
                                 u32 max_positions, SyncResult *__restrict__ result) {
     u32 len = 1;
     // peak #1: the seed (0, 0.0), refined if some corr[i] > 0 turns up within D of position 0
     const u32 seed = result->seed_index;
-    u32 p = seed == kNoSeed ? 0u : first_root(seed, dist, root_list, root_count, nblocks);
+    u32 p = seed == kNoSeed ? 0u : first_root(seed, ri);
     positions[0] = p;
     u64 s = max(static_cast<u64>(p) + dist + 1, 2ull * row);
     while (s < ncorr) {
         const u32 target = static_cast<u32>(s / row);     // peaks.len() after the pushes at s
         for (; len + 1 < target && len < max_positions; ++len) positions[len] = static_cast<u32>(s);
-        p = first_root(static_cast<u32>(s), dist, root_list, root_count, nblocks);
+        p = first_root(static_cast<u32>(s), ri);
         if (len < max_positions) positions[len] = p;
         ++len;
         s = max(static_cast<u64>(p) + dist + 1, static_cast<u64>(row) * (s / row + 1));
@@ -248,13 +252,13 @@ __device__ void pick_sequential(u64 ncorr, u64 nwork, u32 row, u32 dist, const u
     result->status = len < 5 ? 3u /* APT_ERR_FEW_SYNC_FRAMES */ : 0u;
 }
 
-__global__ void k_pick_sequential(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ root_list,
-                                  const u32 *__restrict__ root_count, u32 nblocks, u32 *__restrict__ positions,
+__global__ void k_pick_sequential(u64 ncorr, u64 nwork, u32 row, u32 dist, const RootIndex ri, u32 *__restrict__ positions,
                                   u32 max_positions, SyncResult *__restrict__ result) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    pick_sequential(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions, max_positions, result);
+    if (result->status == kSyncRedo) return;
+    pick_sequential(ncorr, nwork, row, dist, ri, positions, max_positions, result);
     u32 total = 0;
-    for (u32 b = 0; b < nblocks; ++b) total += root_count[b];
+    for (u32 b = 0; b < ri.nblocks; ++b) total += ri.count[b];
     result->n_roots = total;
 }
 
@@ -309,40 +313,50 @@ __device__ __forceinline__ bool last_cta_arrives(u32 *ticket) {
     return s_is_last != 0;
 }
 
-// Exclusive scan of root_count[0..nblocks) into block_off[0..nblocks]; 1024 threads.
+// Exclusive scan of root_count[0..nblocks) into block_off[0..nblocks]; THREADS = blockDim.x.
+template <int THREADS>
 __device__ void scan_root_counts(const u32 *root_count, u32 nblocks, u32 *block_off) {
     __shared__ u32 s_tmp[32];
-    const u32 T = blockDim.x;                 // 512 (k_roots)
+    const u32 T = THREADS;
     const u32 tid = threadIdx.x;
     const u32 per = (nblocks + T - 1) / T;
     const u32 b0 = min(tid * per, nblocks), b1 = min(b0 + per, nblocks);
     u32 local = 0;
     for (u32 b = b0; b < b1; ++b) local += __ldcg(root_count + b);
-    const u32 incl = block_scan_incl<512>(local, 0u, [](u32 x, u32 y) { return x + y; }, s_tmp);
+    const u32 incl = block_scan_incl<THREADS>(local, 0u, [](u32 x, u32 y) { return x + y; }, s_tmp);
     u32 run = incl - local;
     for (u32 b = b0; b < b1; ++b) { block_off[b] = run; run += __ldcg(root_count + b); }
     if (tid == T - 1) block_off[nblocks] = incl;
 }
 
-// smallest root >= s as (dense index, position); s < ncorr guarantees one exists
-__device__ __forceinline__ void first_root_dense(u32 s, u32 dist, u32 nblocks, const u32 *__restrict__ root_list,
-                                                 const u32 *__restrict__ block_off, u32 &dense, u32 &pos) {
-    u32 b = s / dist;
-    const u32 *list = root_list + static_cast<u64>(b) * dist;
-    u32 base = block_off[b];
-    const u32 cnt = block_off[b + 1] - base;
+// smallest root >= s as (dense id, position); s < ncorr guarantees one exists
+__device__ __forceinline__ void first_root_dense(u32 s, const RootIndex &ri, u32 &dense, u32 &pos) {
+    const u32 nblocks = ri.nblocks;
+    u32 b = s / ri.block;
+    const u32 *list = ri_list(ri, b);
+    const u32 cnt = ri.count[b];
     u32 lo = 0, hi = cnt;
     while (lo < hi) {
         const u32 mid = (lo + hi) >> 1;
         if (list[mid] < s) lo = mid + 1; else hi = mid;
     }
-    if (lo < cnt) { dense = base + lo; pos = list[lo]; return; }
+    if (lo < cnt) { dense = ri.base[b] + lo; pos = list[lo]; return; }
     // first root of the next non-empty block
-    const u32 want = block_off[b + 1];
     ++b;
-    while (b < nblocks && block_off[b + 1] == want) ++b;
-    dense = want;
-    pos = b < nblocks ? root_list[static_cast<u64>(b) * dist] : 0xFFFFFFFFu;
+    while (b < nblocks && ri.count[b] == 0) ++b;
+    dense = b < nblocks ? ri.base[b] : 0u;
+    pos = b < nblocks ? ri_list(ri, b)[0] : 0xFFFFFFFFu;
+}
+
+// position of the root with dense id r
+__device__ __forceinline__ u32 root_by_id(u32 r, const RootIndex &ri) {
+    if (ri.by_id) return ri.by_id[r];
+    u32 lo = 0, hi = ri.nblocks;                  // largest b with base[b] <= r (base = exclusive scan of the counts)
+    while (lo + 1 < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (ri.base[mid] <= r) lo = mid; else hi = mid;
+    }
+    return ri_list(ri, lo)[r - ri.base[lo]];
 }
 
 // Grid-wide barrier for a cooperatively launched (co-resident) grid: monotonic arrival counter in global memory
@@ -364,15 +378,16 @@ __device__ __forceinline__ void grid_barrier(u32 *counter, u32 &target) {
 // Cooperative grid (all CTAs co-resident): J0 = F for every candidate, then pointer doubling with one grid
 // barrier per level -- every level is a single pass of <= 1 element per thread, so the cost is the ~12 barriers.
 __global__ void __launch_bounds__(1024)
-k_pick_links(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ root_list,
-             const u32 *__restrict__ root_count, u32 nblocks, u32 *__restrict__ positions, u32 max_positions,
+k_pick_links(u64 ncorr, u64 nwork, u32 row, u32 dist, const RootIndex ri, u32 *__restrict__ positions, u32 max_positions,
              SyncResult *__restrict__ result, PickScratch sc) {
     __shared__ u32 s_tmp[32];
     __shared__ u32 s_misc[4];
     const u32 tid = threadIdx.x;
     constexpr u32 T = 1024;
     const u32 gtid = blockIdx.x * T + tid, gsize = gridDim.x * T;
-    const u32 nroots = __ldcg(sc.block_off + nblocks);
+    const u32 nblocks = ri.nblocks;
+    if (result->status == kSyncRedo) return;          // the record pool overflowed: the host re-runs the sync stage
+    const u32 nroots = __ldcg(ri.nroots);
     const u32 nr = static_cast<u32>((ncorr + row - 1) / row);      // A-type starts row*m < ncorr
     const u32 ncand = nr + nroots;
     const u32 END = ncand;
@@ -380,7 +395,7 @@ k_pick_links(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ ro
     if (ncand + 1 > sc.cap || nr + 1 > max_positions) {
         // too many roots for the scratch (e.g. silence: every index is a root): correct-but-slow path
         if (blockIdx.x == 0 && tid == 0) {
-            pick_sequential(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions, max_positions, result);
+            pick_sequential(ncorr, nwork, row, dist, ri, positions, max_positions, result);
             result->n_roots = nroots;
         }
         return;
@@ -394,19 +409,13 @@ k_pick_links(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ ro
             if (c < nr) {
                 s64 = static_cast<u64>(c) * row;
             } else {
-                const u32 r = c - nr;                      // dense root number -> its block
-                u32 lo = 0, hi = nblocks;                  // largest b with block_off[b] <= r
-                while (lo + 1 < hi) {
-                    const u32 mid = (lo + hi) >> 1;
-                    if (sc.block_off[mid] <= r) lo = mid; else hi = mid;
-                }
-                const u32 rp = root_list[static_cast<u64>(lo) * dist + (r - sc.block_off[lo])];
+                const u32 rp = root_by_id(c - nr, ri);
                 s64 = static_cast<u64>(rp) + dist + 1;
             }
             if (s64 < ncorr) {
                 s = static_cast<u32>(s64);
                 u32 dense;
-                first_root_dense(s, dist, nblocks, root_list, sc.block_off, dense, peak);
+                first_root_dense(s, ri, dense, peak);
                 const u64 sb = static_cast<u64>(peak) + dist + 1;
                 const u64 sa = static_cast<u64>(row) * (s / row + 1);
                 if (max(sa, sb) < ncorr) nxt = sb >= sa ? nr + dense : static_cast<u32>(sa / row);
@@ -423,7 +432,7 @@ k_pick_links(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ ro
         u64 s2 = 2ull * row;
         if (seed != kNoSeed) {
             u32 dense;
-            first_root_dense(seed, dist, nblocks, root_list, sc.block_off, dense, p1);
+            first_root_dense(seed, ri, dense, p1);
             const u64 sb = static_cast<u64>(p1) + dist + 1;
             if (sb >= s2) { s2 = sb; start = nr + dense; }
         }
@@ -466,6 +475,165 @@ k_pick_links(u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *__restrict__ ro
     const u32 nev = s_misc[2];
     const u32 npeaks = nev == 0 ? 1u : __ldcg(sc.cand_s + __ldcg(sc.orbit + nev - 1)) / row;
     // rows that fit (decode.rs:125-127): positions are non-decreasing -> count of the passing prefix
+    u32 cnt = 0;
+    for (u32 i = tid; i + 1 < npeaks; i += T)
+        if (static_cast<u64>(__ldcg(positions + i)) + row < nwork) ++cnt;
+    const u32 total_rows = block_scan_inclusive_1024(cnt, s_tmp);
+    if (tid == T - 1) {
+        result->n_peaks = npeaks;
+        result->n_rows = total_rows;
+        result->status = npeaks < 5 ? 3u : 0u;
+        result->n_roots = nroots;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_pick_cluster: the same orbit walk inside ONE thread-block cluster.  The jump tables live in the distributed
+// shared memory of the cluster's CTAs (node c in CTA c / per), every level ends in a hardware cluster barrier
+// instead of a global-memory grid barrier, and nothing but the root lists, the orbit and the positions touches
+// global memory: ~11 levels of (one DSMEM gather per node + barrier.cluster) instead of 11 grid barriers at
+// ~3.5 us each.  Recordings whose candidates do not fit the cluster's shared memory run the identical code on
+// the global ping-pong tables (slower, still parallel); beyond the scratch capacity: the one-thread walk.
+// ---------------------------------------------------------------------------------------------
+constexpr u32 kPickClusterPer = 24576;       // nodes per CTA: 2 tables x 96 KB of dynamic shared memory
+
+// F for one candidate start c (node numbering: A-type row*m for c < nr, then one B-type per root, END = nr + nroots):
+// start position, the peak the picker ends on from there, and the node it continues from.
+__device__ __forceinline__ void pick_node(u32 c, u32 nr, u32 ncand, u64 ncorr, u32 row, u32 dist, const RootIndex &ri,
+                                          u32 &s, u32 &peak, u32 &nxt) {
+    const u32 END = ncand;
+    nxt = END;
+    s = 0xFFFFFFFFu;
+    peak = 0;
+    if (c >= ncand) return;
+    const u64 s64 = c < nr ? static_cast<u64>(c) * row : static_cast<u64>(root_by_id(c - nr, ri)) + dist + 1;
+    if (s64 >= ncorr) return;
+    s = static_cast<u32>(s64);
+    u32 dense;
+    first_root_dense(s, ri, dense, peak);
+    const u64 sb = static_cast<u64>(peak) + dist + 1;
+    const u64 sa = static_cast<u64>(row) * (s / row + 1);
+    if (max(sa, sb) < ncorr) nxt = sb >= sa ? nr + dense : static_cast<u32>(sa / row);
+}
+
+// J0 for every node, one thread each over the WHOLE GPU (the chains of dependent loads behind F -- root list binary
+// searches -- are latency-bound: 8 CTAs of a cluster would need several rounds of them, 148 SMs need one).
+__global__ void __launch_bounds__(256)
+k_pick_j0(u64 ncorr, u32 row, u32 dist, const RootIndex ri, u32 *__restrict__ positions, u32 max_positions,
+          SyncResult *__restrict__ result, PickScratch sc) {
+    if (result->status == kSyncRedo) return;
+    const u32 nroots = __ldcg(ri.nroots);
+    const u32 nr = static_cast<u32>((ncorr + row - 1) / row);
+    const u32 ncand = nr + nroots;
+    if (ncand + 1 > sc.cap || nr + 1 > max_positions) return;      // k_pick_cluster walks sequentially
+    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c <= ncand) {
+        u32 s, peak, nxt;
+        pick_node(c, nr, ncand, ncorr, row, dist, ri, s, peak, nxt);
+        sc.cand_s[c] = s;
+        sc.cand_peak[c] = peak;
+        sc.ja[c] = nxt;
+    }
+    if (c == 0) {
+        // the first start, from the seed (decode.rs:208-209)
+        const u32 END = ncand;
+        const u32 seed = result->seed_index;
+        u32 p1 = 0, start = END;
+        u64 s2 = 2ull * row;
+        if (seed != kNoSeed) {
+            u32 dense;
+            first_root_dense(seed, ri, dense, p1);
+            const u64 sb = static_cast<u64>(p1) + dist + 1;
+            if (sb >= s2) { s2 = sb; start = nr + dense; }
+        }
+        if (s2 < ncorr) { if (start == END) start = static_cast<u32>(s2 / row); } else start = END;
+        positions[0] = p1;
+        sc.orbit[0] = start;
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+k_pick_cluster(u64 ncorr, u64 nwork, u32 row, u32 dist, const RootIndex ri, u32 *__restrict__ positions, u32 max_positions,
+               SyncResult *__restrict__ result, PickScratch sc) {
+    extern __shared__ u32 pc_tab[];             // [2][kPickClusterPer]
+    __shared__ u32 s_tmp[32];
+    __shared__ u32 s_misc[4];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const u32 CS = cluster.num_blocks(), rank = cluster.block_rank();
+    const u32 tid = threadIdx.x;
+    constexpr u32 T = 1024;
+    constexpr u32 per = kPickClusterPer;
+    const u32 gtid = rank * T + tid, gsize = CS * T;
+    if (result->status == kSyncRedo) return;          // the record pool overflowed: the host re-runs the sync stage
+    const u32 nroots = __ldcg(ri.nroots);
+    const u32 nr = static_cast<u32>((ncorr + row - 1) / row);      // A-type starts row*m < ncorr
+    const u32 ncand = nr + nroots;
+    const u32 END = ncand;
+    if (ncand + 1 > sc.cap || nr + 1 > max_positions) {
+        if (rank == 0 && tid == 0) {
+            pick_sequential(ncorr, nwork, row, dist, ri, positions, max_positions, result);
+            result->n_roots = nroots;
+        }
+        return;
+    }
+    const bool in_smem = ncand + 1 <= CS * per;
+    u32 *gtab[2] = {sc.ja, sc.jb};
+    auto tab_load = [&](u32 which, u32 c) -> u32 {
+        if (in_smem) {
+            const u32 r = c / per;
+            return cluster.map_shared_rank(pc_tab + which * per, r)[c - r * per];
+        }
+        return __ldcg(gtab[which] + c);
+    };
+    // the nodes this thread owns
+    const u32 c_first = in_smem ? rank * per + tid : gtid;
+    const u32 c_limit = in_smem ? min(ncand + 1, (rank + 1) * per) : ncand + 1;
+    const u32 c_step = in_smem ? T : gsize;
+
+    // ---- J0 (k_pick_j0) into the cluster's shared memory ----
+    if (in_smem) {
+        for (u32 c = c_first; c < c_limit; c += c_step) pc_tab[c - rank * per] = __ldcg(sc.ja + c);
+    }
+    cluster.sync();
+
+    // ---- doubling: orbit[n + 2^k] = J_k[orbit[n]];  J_{k+1} = J_k o J_k ----
+    u32 cur = 0;
+    const u32 max_events = min(nr + 1, max_positions);   // every event lands in a new row
+    for (u32 span = 1; span < max_events; span <<= 1) {
+        for (u32 n = gtid; n < span && n + span < max_events; n += gsize) sc.orbit[n + span] = tab_load(cur, __ldcg(sc.orbit + n));
+        if ((span << 1) < max_events) {
+            for (u32 c = c_first; c < c_limit; c += c_step) {
+                const u32 mid = in_smem ? pc_tab[cur * per + (c - rank * per)] : __ldcg(gtab[cur] + c);
+                const u32 v = tab_load(cur, mid);
+                if (in_smem) pc_tab[(cur ^ 1) * per + (c - rank * per)] = v; else gtab[cur ^ 1][c] = v;
+            }
+        }
+        cluster.sync();
+        cur ^= 1;
+    }
+
+    // ---- events -> positions (decode.rs:241-253); END is absorbing so events are a prefix of orbit[] ----
+    for (u32 n = gtid; n < max_events; n += gsize) {
+        const u32 v = __ldcg(sc.orbit + n);
+        if (v == END) continue;
+        const u32 s = __ldcg(sc.cand_s + v);
+        const u32 target = s / row;
+        const u32 prev = n == 0 ? 1u : __ldcg(sc.cand_s + __ldcg(sc.orbit + n - 1)) / row;
+        for (u32 j = prev; j + 1 < target; ++j) positions[j] = s;      // duplicates pushed by the `while`
+        positions[target - 1] = __ldcg(sc.cand_peak + v);
+    }
+    cluster.sync();                                   // also keeps every CTA's tables alive until all remote reads are done
+    if (rank != 0) return;
+
+    // ---- CTA 0: counts ----
+    u32 my_events = 0;
+    for (u32 n = tid; n < max_events; n += T) my_events += __ldcg(sc.orbit + n) != END;
+    const u32 events = block_scan_inclusive_1024(my_events, s_tmp);
+    if (tid == T - 1) s_misc[2] = events;
+    __syncthreads();
+    const u32 nev = s_misc[2];
+    const u32 npeaks = nev == 0 ? 1u : __ldcg(sc.cand_s + __ldcg(sc.orbit + nev - 1)) / row;
     u32 cnt = 0;
     for (u32 i = tid; i + 1 < npeaks; i += T)
         if (static_cast<u64>(__ldcg(positions + i)) + row < nwork) ++cnt;

@@ -12,6 +12,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_lpsync.cuh"
 #include "kernels_sync.cuh"
+#include "kernels_sync2.cuh"
 #include "kernels_ut.cuh"
 
 namespace aptb200 {
@@ -249,9 +250,38 @@ int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32
     return fail(APT_ERR_BAD_ARG, "work rate too high for the sync picker (min_distance %u)", dist);
 }
 
-int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *root_list,
-                const u32 *root_count, u32 nblocks, u32 *positions, u32 max_positions, SyncResult *result,
-                const PickScratch *scratch) {
+int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const RootIndex &ri_in, u32 *positions,
+                u32 max_positions, SyncResult *result, const PickScratch *scratch) {
+    RootIndex ri = ri_in;
+    static const bool force_grid = getenv("APTB200_GRID_PICK") != nullptr;
+    const u64 nr = (ncorr + row - 1) / row;
+    if (scratch && !force_grid && nr <= 20000) {
+        // one 8-CTA cluster, jump tables in distributed shared memory (larger recordings: the whole-GPU cooperative grid)
+        const size_t smem = 2ull * kPickClusterPer * sizeof(u32);
+        static const int attr_ok = [&] {
+            return cudaFuncSetAttribute(k_pick_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) == cudaSuccess;
+        }();
+        if (attr_ok) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(8);
+            cfg.blockDim = dim3(1024);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = c.stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 8;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            PickScratch sc = *scratch;
+            const unsigned j0_grid = (sc.cap + 1 + 255) / 256;      // one thread per possible node; the kernel knows how many exist
+            k_pick_j0<<<j0_grid, 256, 0, c.stream>>>(ncorr, row, dist, ri, positions, max_positions, result, sc);
+            APT_CUDA(cudaGetLastError());
+            APT_CUDA(cudaLaunchKernelEx(&cfg, k_pick_cluster, ncorr, nwork, row, dist, ri, positions, max_positions, result, sc));
+            return APT_OK;
+        }
+    }
     if (scratch) {
         // cooperative launch: the kernel's grid barriers need every CTA resident (1024 threads, no dynamic smem)
         int per_sm = 0;
@@ -259,14 +289,94 @@ int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, con
         const unsigned want = (scratch->cap + 1 + 1023) / 1024;
         const unsigned grid = std::max(1u, std::min(want, static_cast<unsigned>(std::max(per_sm, 1) * c.sm_count)));
         PickScratch sc = *scratch;
-        void *args[] = {&ncorr, &nwork, &row, &dist, &root_list, &root_count, &nblocks, &positions, &max_positions,
-                        &result, &sc};
+        void *args[] = {&ncorr, &nwork, &row, &dist, &ri, &positions, &max_positions, &result, &sc};
         APT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_pick_links), dim3(grid), dim3(1024), args, 0,
                                              c.stream));
     } else {
-        k_pick_sequential<<<1, 32, 0, c.stream>>>(ncorr, nwork, row, dist, root_list, root_count, nblocks, positions,
-                                                  max_positions, result);
+        k_pick_sequential<<<1, 32, 0, c.stream>>>(ncorr, nwork, row, dist, ri, positions, max_positions, result);
     }
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+static LpTaps make_lp_taps(const float *taps_host, u32 ntaps) {
+    LpTaps t{};
+    auto tap = [&](long long j) { return j >= 0 && j < static_cast<long long>(ntaps) ? taps_host[j] : 0.f; };
+    for (int i = 0; i < 32; ++i) {
+        t.a_even[i] = make_float2(tap(2 * i), tap(2 * i - 1));
+        t.a_odd[i] = make_float2(tap(2 * i + 1), tap(2 * i));
+    }
+    return t;
+}
+
+// Rows of 32 low-passed samples per tile of the record kernel (64, or 32 with APTB200_REC_TB=32); fixed per process.
+static int records_tb() {
+    static const int tb = [] {
+        const char *e = getenv("APTB200_REC_TB");
+        return e && atoi(e) == 32 ? 32 : 64;
+    }();
+    return tb;
+}
+
+u32 records_tile(u32 pw) { return static_cast<u32>(rec_tile_outputs(static_cast<int>(pw), records_tb())); }
+
+int launch_lowpass_records(const LaunchCtx &c, const float *e, u64 n, u64 ncorr, const float *taps_host, u32 ntaps, u32 pw,
+                           SyncCtl *ctl, TileDesc *desc, Rec *pool, u32 pool_cap, u32 ntiles) {
+    if (ntiles == 0) return APT_OK;
+    const LpTaps t = make_lp_taps(taps_host, ntaps);
+    const int tb = records_tb();
+    const size_t smem = 2ull * kRecWarps * rec_smem_floats(tb) * sizeof(float);
+    auto launch = [&](auto kern) {
+        static const int per_sm = [&] {
+            int v = 0;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, 32 * kRecWarps, smem) != cudaSuccess || v < 1) v = 1;
+            return v;
+        }();
+        const unsigned want = (ntiles + kRecWarps - 1) / kRecWarps;
+        const unsigned grid = std::min<unsigned>(want, static_cast<unsigned>(c.sm_count) * per_sm);
+        kern<<<grid, 32 * kRecWarps, smem, c.stream>>>(e, n, ncorr, t, ctl, desc, pool, pool_cap, ntiles);
+    };
+    if (tb == 64) {
+        if (ntaps == 37 && pw == 3) launch(k_lowpass_records<37, 3, 64>);
+        else if (ntaps == 43 && pw == 4) launch(k_lowpass_records<43, 4, 64>);
+        else if (ntaps == 61 && pw == 5) launch(k_lowpass_records<61, 5, 64>);
+        else return fail(APT_ERR_BAD_ARG, "no fused low-pass/record kernel for %u taps, pixel width %u", ntaps, pw);
+    } else {
+        if (ntaps == 37 && pw == 3) launch(k_lowpass_records<37, 3, 32>);
+        else if (ntaps == 43 && pw == 4) launch(k_lowpass_records<43, 4, 32>);
+        else if (ntaps == 61 && pw == 5) launch(k_lowpass_records<61, 5, 32>);
+        else return fail(APT_ERR_BAD_ARG, "no fused low-pass/record kernel for %u taps, pixel width %u", ntaps, pw);
+    }
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+int launch_resolve_roots(const LaunchCtx &c, const TileDesc *desc, const Rec *pool, u32 ntiles, u32 tile_w, u32 dist,
+                         u64 ncorr, u32 *root_list, u32 *root_count, u32 *tile_base, u32 *by_id, SyncCtl *ctl,
+                         SyncResult *result) {
+    if (ntiles == 0) return APT_OK;
+    const unsigned grid = (ntiles + kResolveThreads / 32 - 1) / (kResolveThreads / 32);
+    k_resolve_roots<<<grid, kResolveThreads, 0, c.stream>>>(desc, pool, ntiles, tile_w, dist, ncorr, root_list, root_count, tile_base,
+                                                            by_id, ctl, result);
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+int launch_gather_lp(const LaunchCtx &c, const float *e, u64 n, const u32 *positions, const SyncResult *result,
+                     u32 fixed_rows, u32 max_rows, u32 row, u32 px, u32 dec, const float *taps_host, u32 ntaps, float *out) {
+    if (max_rows == 0) return APT_OK;
+    LpFlat lp{};
+    for (u32 i = 0; i < ntaps && i < 64; ++i) lp.c[i] = taps_host[i];
+    const u32 part_px = (px / 2 + 3) / 4 * 4;
+    const u32 eoff = (ntaps - 1 + 3) / 4 * 4;
+    const size_t smem = 2 * (static_cast<size_t>(dec) * part_px + eoff + 8) * sizeof(float);   // double-buffered
+    const unsigned grid = static_cast<unsigned>(std::min<u64>(2ull * max_rows, static_cast<u64>(c.sm_count) * 4));
+    if (ntaps == 37 && dec == 3) k_gather_rows_lp<37, 3><<<grid, kGatherLpThreads, smem, c.stream>>>(e, n, positions, result, fixed_rows, row, px, lp, out);
+    else if (ntaps == 43 && dec == 4) k_gather_rows_lp<43, 4><<<grid, kGatherLpThreads, smem, c.stream>>>(e, n, positions, result, fixed_rows, row, px, lp, out);
+    else if (ntaps == 61 && dec == 5) k_gather_rows_lp<61, 5><<<grid, kGatherLpThreads, smem, c.stream>>>(e, n, positions, result, fixed_rows, row, px, lp, out);
+    else return fail(APT_ERR_BAD_ARG, "no fused gather kernel for %u taps, decimation %u", ntaps, dec);
+    static_assert(kGatherLpThreads * 4 >= 1040, "one pass of a half row");
     APT_CUDA(cudaGetLastError());
     return APT_OK;
 }

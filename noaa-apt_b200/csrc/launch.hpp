@@ -23,6 +23,39 @@ struct SyncResult {
 };
 
 
+// status code the device reports when the record pool of the fused sync stage overflowed: the host re-runs the stage with
+// the legacy kernels (never leaves the library)
+constexpr u32 kSyncRedo = 100;
+
+// Control block of the fused sync stage (kernels_sync2.cuh); zeroed at the start of every job.
+struct SyncCtl {
+    u32 tile_ticket;   // next tile of k_lowpass_records
+    u32 pool_cursor;   // record-pool entries handed out
+    u32 overflow;      // the pool was exhausted
+    u32 root_cursor;   // dense root ids handed out by k_resolve_roots (= number of roots when it is done)
+    u32 pad[4];
+};
+struct TileDesc {      // one per tile of W correlation positions
+    u32 off;           // first pool entry of the tile: ns suffix records, then np prefix records
+    u32 ns, np;
+    float tmax;        // maximum of the correlation over the tile
+};
+struct Rec {
+    u32 pos;           // correlation index
+    float val;
+};
+// Where the picker finds the roots: per block of `block` positions an ascending list.
+struct RootIndex {
+    const u32 *list;
+    const u32 *count;       // [nblocks] roots per block
+    const u32 *base;        // [nblocks] dense id of the block's first root (may be nullptr for the sequential walk)
+    const TileDesc *desc;   // list of block b starts at list + desc[b].off; nullptr: at list + b*block
+    const u32 *by_id;       // root position by dense id; nullptr: `base` is an exclusive scan, found by binary search
+    const u32 *nroots;      // total number of roots
+    u32 block;
+    u32 nblocks;
+};
+
 // Global scratch of the parallel peak picker (k_pick_parallel).
 struct PickScratch {
     u32 *block_off;    // [nblocks + 1] exclusive scan of root_count (dense root numbering)
@@ -116,9 +149,18 @@ int launch_lowpass_corr(const LaunchCtx &c, const float *e, u64 n, const float *
 int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32 *root_list, u32 *root_count,
                  SyncResult *result, const PickScratch *scratch /* nullptr: no dense numbering */);
 // orbit walk -> sync positions (decode.rs:241-253).
-int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const u32 *root_list,
-                const u32 *root_count, u32 nblocks, u32 *positions, u32 max_positions, SyncResult *result,
-                const PickScratch *scratch /* nullptr: sequential walk */);
+int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const RootIndex &ri, u32 *positions,
+                u32 max_positions, SyncResult *result, const PickScratch *scratch /* nullptr: sequential walk */);
+// Fused sync stage (kernels_sync2.cuh): low-pass + correlation + per-tile records, then the roots; f and corr never reach HBM.
+u32 records_tile(u32 pixel_width);   // correlation positions per tile
+int launch_lowpass_records(const LaunchCtx &c, const float *e, u64 n, u64 ncorr, const float *taps_host, u32 ntaps,
+                           u32 pixel_width, SyncCtl *ctl, TileDesc *desc, Rec *pool, u32 pool_cap, u32 ntiles);
+int launch_resolve_roots(const LaunchCtx &c, const TileDesc *desc, const Rec *pool, u32 ntiles, u32 tile_w, u32 dist,
+                         u64 ncorr, u32 *root_list, u32 *root_count, u32 *tile_base, u32 *by_id, SyncCtl *ctl,
+                         SyncResult *result);
+// aligned rows + final decimation with the low-pass evaluated per pixel from the envelope (f never exists in HBM).
+int launch_gather_lp(const LaunchCtx &c, const float *e, u64 n, const u32 *positions, const SyncResult *result,
+                     u32 fixed_rows, u32 max_rows, u32 row, u32 px, u32 dec, const float *taps_host, u32 ntaps, float *out);
 // Bytes of scratch k_pick_parallel needs, and carving of one allocation into a PickScratch.
 size_t pick_scratch_bytes(u32 max_blocks, u32 max_positions, u32 cap);
 PickScratch pick_scratch_carve(void *base, u32 max_blocks, u32 max_positions, u32 cap);

@@ -160,6 +160,14 @@ class Decoder:
         raise_for(self._lib.apt_decoder_last_root_count(self._h, C.byref(r)))
         return {"n_work": a.value, "n_rows": b.value, "n_peaks": c.value, "n_roots": r.value}
 
+    def last_roots(self):
+        n = C.c_size_t(0)
+        raise_for(self._lib.apt_decoder_last_roots(self._h, None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=np.uint64)
+        if n.value:
+            raise_for(self._lib.apt_decoder_last_roots(self._h, out.ctypes.data, out.size, C.byref(n)))
+        return out
+
     def read_stage(self, which):
         idx = {"demodulated": 0, "filtered": 1, "correlation": 2}[which] if isinstance(which, str) else int(which)
         n = C.c_uint64(0)
@@ -207,10 +215,12 @@ def decode_batch(signals, input_rate, settings=None, sync=True, devices=None, st
     lens = (C.c_uint64 * count)(*[x.size for x in xs])
     caps = (C.c_uint64 * count)(*[o.size for o in outs])
     nouts = (C.c_uint64 * count)()
-    statuses = (C.c_int * count)()
+    statuses = (C.c_int * count)(*([_lib.ERR_CUDA] * count))   # never "ok" unless the library says so
     devs = list(devices) if devices else [0]
     dev_arr = (C.c_int * len(devs))(*devs)
-    lib.apt_decode_batch(sig_ptrs, fmt, lens, count, rate, C.byref(s), int(bool(sync)), out_ptrs, caps, nouts,
-                         statuses, dev_arr, len(devs), int(streams_per_device))
+    rc = lib.apt_decode_batch(sig_ptrs, fmt, lens, count, rate, C.byref(s), int(bool(sync)), out_ptrs, caps, nouts,
+                              statuses, dev_arr, len(devs), int(streams_per_device))
+    if rc != _lib.OK and all(int(v) == rc for v in statuses):
+        raise_for(rc)                      # nothing decoded at all (no device, bad settings ...): an error, not a result
     res = [outs[i][: nouts[i]] if statuses[i] == _lib.OK else None for i in range(count)]
     return res, [int(v) for v in statuses]

@@ -118,6 +118,11 @@ def lib():
     L.oracle_map_signal_u8.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_float, C.c_void_p]
     L.oracle_map_signal_u8.restype = None
     L.oracle_quantize_i16.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.oracle_minmax.argtypes = [C.c_void_p, C.c_uint64, fp, fp]
+    L.oracle_percent_buckets.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, fp, fp]
+    L.oracle_percent.argtypes = [C.c_void_p, C.c_uint64, C.c_float, fp, fp]
+    L.oracle_telemetry_rows.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.oracle_read_telemetry.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -304,3 +309,44 @@ def quantize_i16(x):
     out = np.empty(x.size, dtype=np.int16)
     _check(lib().oracle_quantize_i16(x.ctypes.data, x.size, out.ctypes.data))
     return out
+
+
+def minmax(x):
+    x = _f32(x)
+    lo, hi = C.c_float(0), C.c_float(0)
+    _check(lib().oracle_minmax(x.ctypes.data, x.size, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
+def percent_buckets(x):
+    x = _f32(x)
+    b = np.zeros(1000, dtype=np.uint32)
+    lo, hi = C.c_float(0), C.c_float(0)
+    _check(lib().oracle_percent_buckets(x.ctypes.data, x.size, b.ctypes.data, C.byref(lo), C.byref(hi)))
+    return b, lo.value, hi.value
+
+
+def percent(x, p):
+    """misc.rs:119-175"""
+    x = _f32(x)
+    lo, hi = C.c_float(0), C.c_float(0)
+    _check(lib().oracle_percent(x.ctypes.data, x.size, p, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
+def telemetry_rows(x):
+    """telemetry.rs:147-170 -> (mean_a, mean_b, variance), one value per image row"""
+    x = _f32(x)
+    rows = x.size // 2080
+    a, b, v = (np.empty(rows, dtype=np.float32) for _ in range(3))
+    _check(lib().oracle_telemetry_rows(x.ctypes.data, x.size, a.ctypes.data, b.ctypes.data, v.ctypes.data))
+    return a, b, v
+
+
+def read_telemetry(x):
+    """telemetry.rs:125-243 -> (wedges_a[16], wedges_b[16], best_row)"""
+    x = _f32(x)
+    wa, wb = np.empty(16, dtype=np.float32), np.empty(16, dtype=np.float32)
+    best = C.c_uint64(0)
+    _check(lib().oracle_read_telemetry(x.ctypes.data, x.size, wa.ctypes.data, wb.ctypes.data, C.byref(best)))
+    return wa, wb, best.value

@@ -506,3 +506,137 @@ int oracle_quantize_i16(const float *x, uint64_t n, int16_t *out) {
     }
     return ORACLE_OK;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Next-row (f)3: contrast bounds and telemetry statistics of the decoded image (after the hot path).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* dsp.rs:20-54 get_min / get_max: first-wins strict comparisons */
+static float sig_min(const float *x, uint64_t n) {
+    float m = x[0];
+    for (uint64_t i = 0; i < n; ++i) if (x[i] < m) m = x[i];
+    return m;
+}
+static float sig_max(const float *x, uint64_t n) {
+    float m = x[0];
+    for (uint64_t i = 0; i < n; ++i) if (x[i] > m) m = x[i];
+    return m;
+}
+
+int oracle_minmax(const float *x, uint64_t n, float *low, float *high) {
+    if (n == 0) return ORACLE_ERR_BAD_ARG;                 /* Internal("Can't get maximum of a zero length vector") */
+    *low = sig_min(x, n);
+    *high = sig_max(x, n);
+    return ORACLE_OK;
+}
+
+/* misc.rs:119-175 percent(): 1000 buckets between min and max; buckets[trunc((x-min)/range*1000)] clamped */
+int oracle_percent_buckets(const float *x, uint64_t n, uint32_t *buckets /* [1000] */, float *mn, float *mx) {
+    if (n == 0) return ORACLE_ERR_BAD_ARG;
+    const float min = sig_min(x, n), max = sig_max(x, n);
+    const float total_range = max - min;
+    memset(buckets, 0, 1000 * sizeof(uint32_t));
+    for (uint64_t i = 0; i < n; ++i) {
+        const float t = truncf((x[i] - min) / total_range * 1000.f);
+        /* `as usize` saturates: negative / NaN -> 0, huge -> usize::MAX; then .max(0).min(999) */
+        uint32_t b;
+        if (!(t >= 0.f)) b = 0;
+        else if (t >= 999.f) b = 999;
+        else b = (uint32_t)t;
+        buckets[b] += 1;
+    }
+    *mn = min;
+    *mx = max;
+    return ORACLE_OK;
+}
+
+int oracle_percent(const float *x, uint64_t n, float percent, float *low, float *high) {
+    if (percent < 0.f || percent > 1.f) return ORACLE_ERR_BAD_ARG;   /* Internal("Percent given should be between 0 and 1") */
+    uint32_t buckets[1000];
+    float min, max;
+    int rc = oracle_percent_buckets(x, n, buckets, &min, &max);
+    if (rc != ORACLE_OK) return rc;
+    const float remainder = (1.f - percent) / 2.f;
+    const float total_range = max - min;
+    uint32_t accum = 0;
+    int low_bucket = -1, high_bucket = -1;
+    for (int b = 0; b < 1000; ++b) {
+        accum += buckets[b];
+        const float frac = (float)accum / (float)n;
+        if (low_bucket < 0 && frac > remainder) low_bucket = b;
+        else if (high_bucket < 0 && frac > 1.f - remainder) high_bucket = b;
+    }
+    if (high_bucket < 0) high_bucket = 999;
+    if (low_bucket < 0) return ORACLE_ERR_BAD_ARG;          /* low_bucket.unwrap() panics */
+    *low = (float)low_bucket / 1000.f * total_range + min;
+    *high = (float)high_bucket / 1000.f * total_range + min;
+    return ORACLE_OK;
+}
+
+/* telemetry.rs:147-170: per image row the means of the two telemetry bands and their pooled variance */
+int oracle_telemetry_rows(const float *x, uint64_t n, float *mean_a, float *mean_b, float *variance) {
+    const uint64_t rows = n / 2080;
+    for (uint64_t r = 0; r < rows; ++r) {
+        const float *line = x + r * 2080;
+        const float *a = line + 994, *b = line + 2034;
+        float sa = 0.f, sb = 0.f;
+        for (int i = 0; i < 44; ++i) sa += a[i];
+        for (int i = 0; i < 44; ++i) sb += b[i];
+        const float ma = sa / 44.f, mb = sb / 44.f;
+        float va = 0.f, vb = 0.f;
+        for (int i = 0; i < 44; ++i) { const float d = a[i] - ma; va += d * d; }
+        for (int i = 0; i < 44; ++i) { const float d = b[i] - mb; vb += d * d; }
+        mean_a[r] = ma;
+        mean_b[r] = mb;
+        variance[r] = (va + vb) / 88.f;
+    }
+    return ORACLE_OK;
+}
+
+/* telemetry.rs:125-243 read_telemetry + :30-66 Telemetry::from_bands: the best frame start and the 16 wedge values of
+ * each channel; contrast bounds are low = wedge 9, high = wedge 8 averaged over both channels (noaa_apt.rs:143-149). */
+int oracle_read_telemetry(const float *x, uint64_t n, float *wedges_a /* [16] */, float *wedges_b /* [16] */,
+                          uint64_t *best_row) {
+    static const float pattern[25] = {31.f, 63.f, 95.f, 127.f, 159.f, 191.f, 224.f, 255.f, 0.f,
+                                      0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f,
+                                      31.f, 63.f, 95.f, 127.f, 159.f, 191.f, 224.f, 255.f, 0.f};
+    float sample[200];
+    for (int i = 0; i < 200; ++i) sample[i] = pattern[i / 8];
+    const uint64_t rows = n / 2080;
+    if (rows < 200) return ORACLE_ERR_TOO_SHORT;           /* Internal("Recording too short for telemetry decoding") */
+    float *ma = (float *)malloc(rows * sizeof(float)), *mb = (float *)malloc(rows * sizeof(float)),
+          *var = (float *)malloc(rows * sizeof(float));
+    if (!ma || !mb || !var) { free(ma); free(mb); free(var); return ORACLE_ERR_NOMEM; }
+    oracle_telemetry_rows(x, n, ma, mb, var);
+    uint64_t best = 0;
+    float best_q = 0.f;
+    for (uint64_t i = 0; i + 200 < rows; ++i) {
+        float sum = 0.f;
+        for (int j = 0; j < 200; ++j) {
+            sum += sample[j] * ma[i + j];
+            sum += sample[j] * mb[i + j];
+        }
+        float dev = 0.f;
+        for (int j = 0; j < 200; ++j) dev += sqrtf(var[i + j]);
+        const float q = sum / dev;
+        if (q > best_q) { best = i; best_q = q; }
+    }
+    /* from_bands: means of 8 contiguous rows from `best`, 16 + 9 wedges (fewer if the image ends) */
+    float wa[25], wb[25];
+    int nw = 0;
+    for (; nw < 25 && best + 8ull * (nw + 1) <= rows; ++nw) {
+        float sa = 0.f, sb = 0.f;
+        for (int k = 0; k < 8; ++k) sa += ma[best + 8 * nw + k];
+        for (int k = 0; k < 8; ++k) sb += mb[best + 8 * nw + k];
+        wa[nw] = sa / 8.f;
+        wb[nw] = sb / 8.f;
+    }
+    free(ma); free(mb); free(var);
+    if (nw < 25) return ORACLE_ERR_BAD_ARG;                /* index out of bounds panic in from_bands */
+    for (int w = 1; w <= 16; ++w) {
+        wedges_a[w - 1] = w <= 9 ? (wa[w - 1] + wa[w + 15]) / 2.f : wa[w - 1];
+        wedges_b[w - 1] = w <= 9 ? (wb[w - 1] + wb[w + 15]) / 2.f : wb[w - 1];
+    }
+    *best_row = best;
+    return ORACLE_OK;
+}

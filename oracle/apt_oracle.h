@@ -133,6 +133,15 @@ void oracle_map_signal_u8(const float *x, uint64_t n, float low, float high, uin
 /* wav.rs:71-85: normalise by max and quantise to i16 (resample tool path). */
 int oracle_quantize_i16(const float *x, uint64_t n, int16_t *out);
 
+/* Next-row (f)3 -- contrast bounds and telemetry statistics of the decoded image:
+ * dsp.rs:20-54 get_min/get_max; misc.rs:119-175 percent() (and its 1000 bucket counts);
+ * telemetry.rs:147-170 per-row band means + variance; telemetry.rs:125-243 + :30-66 frame search and wedge values. */
+int oracle_minmax(const float *x, uint64_t n, float *low, float *high);
+int oracle_percent_buckets(const float *x, uint64_t n, uint32_t *buckets, float *mn, float *mx);
+int oracle_percent(const float *x, uint64_t n, float percent, float *low, float *high);
+int oracle_telemetry_rows(const float *x, uint64_t n, float *mean_a, float *mean_b, float *variance);
+int oracle_read_telemetry(const float *x, uint64_t n, float *wedges_a, float *wedges_b, uint64_t *best_row);
+
 #ifdef __cplusplus
 }
 #endif

@@ -326,3 +326,46 @@ def test_chunked_upload_of_long_recordings(rate, monkeypatch):
     assert np.array_equal(got, whole)
     assert got.size == ref.size and nerr(got, ref) <= TOL
     assert got16.size == ref.size and nerr(got16, ref) <= TOL
+
+
+# ------------------------------------------------------------------------------- fused sync stage
+
+def _roots_direct(corr, dist):
+    """Definition of a root: no corr[j] > corr[p] for j in (p, p + dist]."""
+    n = corr.size
+    pad = np.concatenate([corr, np.full(dist, -np.inf, np.float32)])
+    w = np.lib.stride_tricks.sliding_window_view(pad[1:], dist).max(axis=1)[:n]
+    return np.nonzero(~(w > corr))[0].astype(np.uint64)
+
+
+@pytest.mark.parametrize("rate,profile,seconds", [(48000, "standard", 30), (11025, "standard", 40), (48000, "fast", 16),
+                                                  (48000, "slow", 16)])
+def test_fused_sync_stage_roots_match_definition(rate, profile, seconds):
+    """kernels_sync2.cuh: the roots that come out of the per-tile records (f and corr never written) must be exactly the
+    roots of the correlation the legacy kernel writes (same arithmetic, bit-identical values) by the definition."""
+    x = synth.apt_signal(rate, seconds, seed=17)
+    settings = na.Settings.profile(profile)
+    with na.Decoder(rate, settings, max_samples=x.size) as dec:
+        dec.decode(x)
+        roots = dec.last_roots()
+        corr = dec.read_stage("correlation")          # materialised on demand by k_lowpass_corr
+    dist = (2080 * settings.work_rate // 4160) * 8 // 10
+    assert np.array_equal(roots, _roots_direct(corr, dist))
+
+
+def test_fused_sync_stage_pool_overflow_redo(monkeypatch):
+    """Silence: every index is a record, the pool overflows, wait() re-runs the sync stage with the legacy kernels."""
+    rate = 48000
+    x = synth.apt_signal(rate, 12, seed=5)
+    x[x.size // 2:] = 0.0
+    ref, st = oracle.decode_steps(x, rate)
+    monkeypatch.setenv("APTB200_RECORD_POOL", "4096")
+    with na.Decoder(rate, na.Settings(), max_samples=x.size) as dec:
+        got = dec.decode(x)
+        assert np.array_equal(dec.last_sync(), st["sync_pos"])
+    assert got.size == ref.size and nerr(got, ref) <= TOL
+    monkeypatch.delenv("APTB200_RECORD_POOL")
+    with na.Decoder(rate, na.Settings(), max_samples=x.size) as dec:
+        got = dec.decode(x)
+        assert np.array_equal(dec.last_sync(), st["sync_pos"])
+    assert got.size == ref.size and nerr(got, ref) <= TOL
