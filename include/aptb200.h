@@ -158,6 +158,40 @@ void apt_cache_clear(void);
 int apt_decode_pcm16(const int16_t *pcm, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
                      float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user);
 
+/* ------------------------------------------ image stage (after decode, on the device) */
+
+/* The front of noaa_apt::process (noaa_apt.rs:132-190): contrast bounds, then map_signal_u8 (noaa_apt.rs:249-259).  The
+ * rows stay on the device until they are u8 (4x fewer bytes leave the GPU).  Given the same f32 rows the results are
+ * bit-identical to the reference's (every f32 operation rounded on its own, the reference's summation order). */
+typedef enum apt_contrast {
+    APT_CONTRAST_MINMAX = 0,      /* Contrast::MinMax: dsp::get_min / get_max             noaa_apt.rs:157-163, dsp.rs:20-54  */
+    APT_CONTRAST_PERCENT = 1,     /* Contrast::Percent(p): misc::percent, 1000 buckets    misc.rs:119-175                    */
+    APT_CONTRAST_TELEMETRY = 2    /* Contrast::Telemetry: wedges 9 / 8 of the best frame  noaa_apt.rs:141-149, telemetry.rs  */
+} apt_contrast;
+
+typedef struct apt_image_info {
+    float low, high;              /* contrast bounds: `low` maps to 0, `high` to 255 */
+    uint64_t rows;                /* image height (width is 2080) */
+    uint64_t telemetry_row;       /* telemetry: row where the best frame starts (telemetry.rs:192-221) */
+    float wedges_a[16], wedges_b[16];   /* telemetry: Telemetry::values_a / values_b (telemetry.rs:30-66) */
+} apt_image_info;
+
+/* decode() + contrast + map_signal_u8 in one call: out receives rows*2080 u8 pixels (cap in bytes >= apt_decode_len_bound).
+ * format: apt_sample_format of `signal` (f32 Signal or the WAV's PCM16).  Errors of the image stage: the reference's
+ * Internal("Recording too short for telemetry decoding") and its panics (empty image, frame running off the image) come
+ * back as APT_ERR_TOO_SHORT / APT_ERR_BAD_ARG. */
+int apt_decode_image_u8(const void *signal, int format, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
+                        int contrast, float percent, uint8_t *out, uint64_t cap, uint64_t *nout, apt_image_info *info,
+                        apt_status_cb cb, void *user);
+
+/* Stage entry points on host buffers (rows = decode()'s output, n = rows*2080 values). */
+/* noaa_apt::map_signal_u8 -- noaa_apt.rs:249-259. */
+int apt_map_signal_u8(const float *signal, uint64_t n, float low, float high, uint8_t *out);
+/* Contrast bounds of an image: MinMax / misc::percent / telemetry (info receives bounds, wedges, frame row). */
+int apt_contrast_bounds(const float *signal, uint64_t n, int contrast, float percent, apt_image_info *info);
+/* telemetry.rs:147-170: per-row means of the two telemetry bands and their pooled variance (n / 2080 values each). */
+int apt_telemetry_rows(const float *signal, uint64_t n, float *mean_a, float *mean_b, float *variance);
+
 /* ----------------------------------------------- decoder object (streams) */
 
 typedef struct apt_decoder apt_decoder;
@@ -180,6 +214,11 @@ int apt_decoder_submit_device(apt_decoder *dec, const void *signal, int format, 
                               float *out, uint64_t cap);
 int apt_decoder_submit_host(apt_decoder *dec, const void *signal, int format, uint64_t n, int sync,
                             float *out, uint64_t cap);
+/* Image mode of a decoder: contrast >= 0 (apt_contrast) makes every following submit produce the u8 image instead of the
+ * f32 rows -- `out` is then a uint8_t buffer and `cap` / *nout count bytes; contrast < 0 switches back to f32 rows. */
+int apt_decoder_set_image_mode(apt_decoder *dec, int contrast, float percent);
+/* Contrast bounds / telemetry of the last image job (after apt_decoder_wait). */
+int apt_decoder_image_info(apt_decoder *dec, apt_image_info *info);
 /* 1 if the decoder's job has finished (apt_decoder_wait will not block) or none is in flight, else 0. */
 int apt_decoder_poll(apt_decoder *dec);
 /* Block until the job is finished; returns its status (APT_ERR_FEW_SYNC_FRAMES etc.) and *nout. */

@@ -56,6 +56,13 @@ class CUtInfo(C.Structure):
                                           "stream_b", "halo_u0", "halo_n", "chunk_len")] + [("cs", C.c_uint32 * 8), ("ce", C.c_uint32 * 8)]
 
 
+class CImageInfo(C.Structure):
+    _fields_ = [("low", C.c_float), ("high", C.c_float), ("rows", C.c_uint64), ("telemetry_row", C.c_uint64),
+                ("wedges_a", C.c_float * 16), ("wedges_b", C.c_float * 16)]
+
+
+CONTRAST_MINMAX, CONTRAST_PERCENT, CONTRAST_TELEMETRY = 0, 1, 2
+
 STATUS_CB = C.CFUNCTYPE(None, C.c_float, C.c_char_p, C.c_void_p)
 
 # name -> (restype, argtypes); every symbol include/aptb200.h declares.
@@ -87,6 +94,13 @@ SIGNATURES = {
                              C.c_void_p, C.c_uint64, _u64p, STATUS_CB, C.c_void_p]),
     "apt_decode_pcm16": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(CSettings), C.c_int,
                                    C.c_void_p, C.c_uint64, _u64p, STATUS_CB, C.c_void_p]),
+    "apt_decode_image_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint32, C.POINTER(CSettings), C.c_int, C.c_int,
+                                      C.c_float, C.c_void_p, C.c_uint64, _u64p, C.POINTER(CImageInfo), STATUS_CB, C.c_void_p]),
+    "apt_map_signal_u8": (C.c_int, [C.c_void_p, C.c_uint64, C.c_float, C.c_float, C.c_void_p]),
+    "apt_contrast_bounds": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.POINTER(CImageInfo)]),
+    "apt_telemetry_rows": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "apt_decoder_set_image_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
+    "apt_decoder_image_info": (C.c_int, [C.c_void_p, C.POINTER(CImageInfo)]),
     "apt_decoder_create": (C.c_int, [C.c_int, C.c_uint32, C.POINTER(CSettings), C.c_uint64, C.POINTER(C.c_void_p)]),
     "apt_decoder_destroy": (None, [C.c_void_p]),
     "apt_decoder_submit_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64]),

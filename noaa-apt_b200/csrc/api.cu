@@ -1,6 +1,8 @@
 // C ABI (include/aptb200.h) over the decoder object and the stage kernels.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -65,6 +67,9 @@ int free_decoder_buffers(apt_decoder *d) {
         if (p) cudaFree(p);
     if (d->h_res) cudaFreeHost(d->h_res);
     if (d->h_out) cudaFreeHost(d->h_out);
+    if (d->h_post) cudaFreeHost(d->h_post);
+    for (void *p : {(void *)d->d_post, (void *)d->d_tel, (void *)d->d_out8})
+        if (p) cudaFree(p);
     d->own_stager.reset();
     for (auto e : d->ev_begin) cudaEventDestroy(e);
     for (auto e : d->ev_end) cudaEventDestroy(e);
@@ -482,6 +487,21 @@ extern "C" void apt_decoder_destroy(apt_decoder *dec) {
 
 namespace {
 
+// contrast bounds + u8 map of the rows the job leaves in d_out; the head of the control block follows the job to the host
+int enqueue_image_stage(apt_decoder *d, unsigned char *out8) {
+    const Plan &p = d->plan;
+    const LaunchCtx c{d->stream, d->sm_count};
+    const u32 max_rows = static_cast<u32>(std::max<uint64_t>(d->max_out / kPxPerRow, 1));
+    const u32 fixed = d->job_sync ? 0u : static_cast<u32>(d->job_fixed_out / kPxPerRow);
+    (void)p;
+    APT_TRY(launch_image_stage(c, d->d_out, d->job_sync ? d->d_res : nullptr, fixed, max_rows, kPxPerRow, d->image_contrast,
+                               d->image_percent, d->d_post, d->d_tel, d->d_tel + max_rows, d->d_tel + 2 * static_cast<size_t>(max_rows),
+                               nullptr, out8, false));
+    d->launches += d->image_contrast == APT_CONTRAST_PERCENT ? 4 : 3;
+    APT_CUDA(cudaMemcpyAsync(d->h_post, d->d_post, offsetof(PostCtl, buckets), cudaMemcpyDeviceToHost, d->stream));
+    return APT_OK;
+}
+
 int submit_common(apt_decoder *d, const void *signal, int format, uint64_t n, int sync, float *out, uint64_t cap,
                   bool host) {
     if (!d) return fail(APT_ERR_BAD_ARG, "null decoder");
@@ -512,7 +532,21 @@ int submit_common(apt_decoder *d, const void *signal, int format, uint64_t n, in
         return fail(APT_ERR_BAD_ARG, "work_rate %u is too high for the sync picker (min_distance %u > 16384); decode without "
                                      "sync or use a work_rate <= 37440", p.st.work_rate, p.dist);
     const uint64_t need = d->job_sync ? (nwork / p.row) * kPxPerRow : plan_out_bound(p, n);
-    if (!out || cap < need) return fail(APT_ERR_CAPACITY, "output needs room for %llu floats", (unsigned long long)need);
+    if (!out || cap < need) return fail(APT_ERR_CAPACITY, "output needs room for %llu %s", (unsigned long long)need,
+                                        d->image_contrast >= 0 ? "bytes" : "floats");
+    d->job_image = d->image_contrast >= 0;
+    if (d->job_image) {
+        if (!p.work_multiple) return fail(APT_ERR_BAD_ARG, "the image stage needs rows of 2080 pixels (work_rate multiple of 4160)");
+        const uint64_t max_rows = std::max<uint64_t>(d->max_out / kPxPerRow, 1);
+        if (!d->d_post) {
+            APT_CUDA(cudaMalloc(&d->d_post, sizeof(PostCtl)));
+            APT_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&d->h_post), sizeof(PostCtl), cudaHostAllocDefault));
+            APT_CUDA(cudaMalloc(&d->d_tel, 3 * max_rows * sizeof(float)));
+        }
+        if (!d->d_out) APT_CUDA(cudaMalloc(&d->d_out, std::max<uint64_t>(d->max_out, 1) * sizeof(float)));
+        if (host && !d->d_out8) APT_CUDA(cudaMalloc(&d->d_out8, std::max<uint64_t>(d->max_out, 1)));
+    }
+    const size_t elem = d->job_image ? 1 : sizeof(float);
 
     const void *dev_in = signal;
     float *rows_dst = out;
@@ -530,7 +564,7 @@ int submit_common(apt_decoder *d, const void *signal, int format, uint64_t n, in
         }
         if (d->job_out_pageable && !d->h_out)
             APT_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&d->h_out), std::max<uint64_t>(d->max_out, 1) * sizeof(float),
-                                   cudaHostAllocDefault));
+                                   cudaHostAllocDefault));   // sized for f32 rows: also holds the u8 image
         // Recordings longer than the chunk size are uploaded in chunks that overlap the resampling; shorter ones
         // (and the L == 1 first stage) are staged whole.
         const bool chunked = d->chunk_samples != 0 && n > d->chunk_samples && p.first_polyphase;
@@ -565,8 +599,10 @@ int submit_common(apt_decoder *d, const void *signal, int format, uint64_t n, in
         }
         rows_dst = d->d_out;
     }
+    if (d->job_image) rows_dst = d->d_out;      // the f32 rows are an intermediate of the image job
     d->job_rows_src = rows_dst;
     int st = decoder_enqueue(d, dev_in, format, n, sync, rows_dst, host_chunked);
+    if (st == APT_OK && d->job_image) st = enqueue_image_stage(d, host ? d->d_out8 : reinterpret_cast<unsigned char *>(out));
     if (st != APT_OK) {
         cudaStreamSynchronize(d->stream);
         d->job_status = st;
@@ -579,8 +615,9 @@ int submit_common(apt_decoder *d, const void *signal, int format, uint64_t n, in
         // (at most one row more than is produced)
         d->job_d2h_floats = d->job_sync ? need : d->job_fixed_out;
         if (d->job_d2h_floats)
-            APT_CUDA(cudaMemcpyAsync(d->job_out_pageable ? d->h_out : out, d->d_out, d->job_d2h_floats * sizeof(float),
-                                     cudaMemcpyDeviceToHost, d->stream));
+            APT_CUDA(cudaMemcpyAsync(d->job_out_pageable ? static_cast<void *>(d->h_out) : static_cast<void *>(out),
+                                     d->job_image ? static_cast<const void *>(d->d_out8) : static_cast<const void *>(d->d_out),
+                                     d->job_d2h_floats * elem, cudaMemcpyDeviceToHost, d->stream));
     }
     d->in_flight = true;
     return APT_OK;
@@ -604,7 +641,10 @@ extern "C" int apt_decoder_wait(apt_decoder *d, uint64_t *nout) {
     if (!d->in_flight) return d->job_status;
     APT_CUDA(cudaSetDevice(d->device));
     d->in_flight = false;
+    static const bool trace = getenv("APTB200_TRACE_HOST") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
     APT_CUDA(cudaStreamSynchronize(d->stream));
+    const auto t_synced = std::chrono::steady_clock::now();
     uint64_t produced = d->job_fixed_out;
     d->last_work = d->job_work;
     d->last_peaks = 0;
@@ -614,10 +654,13 @@ extern "C" int apt_decoder_wait(apt_decoder *d, uint64_t *nout) {
             // the record pool of the fused stage overflowed (silence, ramps: every index a record): the sync stage runs
             // again with the legacy kernels on the envelope that is still in d_e
             APT_TRY(redo_sync_legacy(d));
+            if (d->job_image)
+                APT_TRY(enqueue_image_stage(d, d->job_host ? d->d_out8 : reinterpret_cast<unsigned char *>(d->job_out)));
             APT_CUDA(cudaMemcpyAsync(d->h_res, d->d_res, sizeof(SyncResult), cudaMemcpyDeviceToHost, d->stream));
             if (d->job_host && d->job_d2h_floats)
-                APT_CUDA(cudaMemcpyAsync(d->job_out_pageable ? d->h_out : d->job_out, d->d_out, d->job_d2h_floats * sizeof(float),
-                                         cudaMemcpyDeviceToHost, d->stream));
+                APT_CUDA(cudaMemcpyAsync(d->job_out_pageable ? static_cast<void *>(d->h_out) : static_cast<void *>(d->job_out),
+                                         d->job_image ? static_cast<const void *>(d->d_out8) : static_cast<const void *>(d->d_out),
+                                         d->job_d2h_floats * (d->job_image ? 1 : sizeof(float)), cudaMemcpyDeviceToHost, d->stream));
             APT_CUDA(cudaStreamSynchronize(d->stream));
             d->last_fused = false;
         }
@@ -630,9 +673,29 @@ extern "C" int apt_decoder_wait(apt_decoder *d, uint64_t *nout) {
         }
         produced = static_cast<uint64_t>(res.n_rows) * kPxPerRow;
     }
+    const size_t elem = d->job_image ? 1 : sizeof(float);
     if (d->job_host && d->job_out_pageable && produced) {
-        if (d->stager) d->stager->scatter(d->job_out, d->h_out, produced * sizeof(float));
-        else memcpy(d->job_out, d->h_out, produced * sizeof(float));
+        if (d->stager) d->stager->scatter(d->job_out, d->h_out, produced * elem);
+        else memcpy(d->job_out, d->h_out, produced * elem);
+    }
+    if (trace)
+        fprintf(stderr, "[aptb200 host] wait: stream sync %.2f ms, copy-out %.2f ms (%s)\n",
+                std::chrono::duration<double>(t_synced - t_begin).count() * 1e3,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_synced).count() * 1e3,
+                d->job_out_pageable ? "pageable" : "direct");
+    if (d->job_image) {
+        const PostCtl &pc = *d->h_post;
+        apt_image_info &ii = d->last_image;
+        ii.low = pc.low;
+        ii.high = pc.high;
+        ii.rows = pc.rows;
+        ii.telemetry_row = pc.telemetry_row;
+        memcpy(ii.wedges_a, pc.wedges_a, sizeof(ii.wedges_a));
+        memcpy(ii.wedges_b, pc.wedges_b, sizeof(ii.wedges_b));
+        if (pc.status == 3) d->job_status = fail(APT_ERR_TOO_SHORT, "Recording too short for telemetry decoding");
+        else if (pc.status != 0) d->job_status = fail(APT_ERR_BAD_ARG, "image stage: %s", pc.status == 1 ? "empty image" :
+                                                      pc.status == 2 ? "no contrast bucket found" : "telemetry frame runs off the image");
+        if (d->job_status != APT_OK) return d->job_status;
     }
     d->last_rows = d->plan.work_multiple ? produced / kPxPerRow : 0;
     d->last_out = produced;
@@ -641,6 +704,23 @@ extern "C" int apt_decoder_wait(apt_decoder *d, uint64_t *nout) {
         for (int i = 0; i < d->ev_used; ++i) cudaEventElapsedTime(&d->kernel_ms[i], d->ev_begin[i], d->ev_end[i]);
     }
     if (nout) *nout = produced;
+    return APT_OK;
+}
+
+extern "C" int apt_decoder_set_image_mode(apt_decoder *d, int contrast, float percent) {
+    if (!d) return fail(APT_ERR_BAD_ARG, "null decoder");
+    if (d->in_flight) return fail(APT_ERR_BAD_ARG, "decoder has a job in flight");
+    if (contrast > APT_CONTRAST_TELEMETRY) return fail(APT_ERR_BAD_ARG, "unknown contrast mode %d", contrast);
+    if (contrast == APT_CONTRAST_PERCENT && !(percent >= 0.f && percent <= 1.f))
+        return fail(APT_ERR_BAD_ARG, "Percent given should be between 0 and 1");      // misc.rs:120-124
+    d->image_contrast = contrast;
+    d->image_percent = percent;
+    return APT_OK;
+}
+
+extern "C" int apt_decoder_image_info(apt_decoder *d, apt_image_info *info) {
+    if (!d || !info) return fail(APT_ERR_BAD_ARG, "null argument");
+    *info = d->last_image;
     return APT_OK;
 }
 
@@ -848,8 +928,26 @@ void cache_put(int device, uint32_t rate, const apt_settings &st, apt_decoder *d
     if (victim) apt_decoder_destroy(victim);
 }
 
+// batch feeders park all their decoders (several per key)
+void cache_put_multi(int device, uint32_t rate, const apt_settings &st, apt_decoder *d) {
+    apt_decoder *victim = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mutex);
+        if (g_cache.size() >= kCacheMaxIdle) {
+            size_t lru = 0;
+            for (size_t i = 1; i < g_cache.size(); ++i)
+                if (g_cache[i].stamp < g_cache[lru].stamp) lru = i;
+            victim = g_cache[lru].dec;
+            g_cache.erase(g_cache.begin() + static_cast<long>(lru));
+        }
+        g_cache.push_back(CacheEntry{device, rate, st, d, ++g_cache_stamp});
+    }
+    if (victim) apt_decoder_destroy(victim);
+}
+
 int decode_oneshot(const void *signal, int format, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
-                   float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user) {
+                   float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user, int contrast = -1,
+                   float percent = 0.f, apt_image_info *info = nullptr) {
     if (!s || !nout) return fail(APT_ERR_BAD_ARG, "null argument");
     *nout = 0;
     if (n == 0 || !signal) return fail(APT_ERR_BAD_ARG, "empty signal");
@@ -873,8 +971,12 @@ int decode_oneshot(const void *signal, int format, uint64_t n, uint32_t input_ra
     }
     d->cb = cb;
     d->cb_user = user;
+    d->image_contrast = contrast;
+    d->image_percent = percent;
     int st = apt_decoder_submit_host(d, signal, format, n, sync, out, cap);
     if (st == APT_OK) st = apt_decoder_wait(d, nout);
+    if (st == APT_OK && info) *info = d->last_image;
+    d->image_contrast = -1;
     d->cb = nullptr;
     d->cb_user = nullptr;
     if (use_cache) cache_put(device, input_rate, *s, d);
@@ -906,6 +1008,92 @@ extern "C" int apt_decode(const float *signal, uint64_t n, uint32_t input_rate, 
 extern "C" int apt_decode_pcm16(const int16_t *pcm, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
                                 float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user) {
     return decode_oneshot(pcm, APT_PCM16, n, input_rate, s, sync, out, cap, nout, cb, user);
+}
+
+// ============================================================================== image stage
+
+extern "C" int apt_decode_image_u8(const void *signal, int format, uint64_t n, uint32_t input_rate, const apt_settings *s,
+                                   int sync, int contrast, float percent, uint8_t *out, uint64_t cap, uint64_t *nout,
+                                   apt_image_info *info, apt_status_cb cb, void *user) {
+    if (contrast < 0 || contrast > APT_CONTRAST_TELEMETRY) return fail(APT_ERR_BAD_ARG, "unknown contrast mode %d", contrast);
+    if (contrast == APT_CONTRAST_PERCENT && !(percent >= 0.f && percent <= 1.f))
+        return fail(APT_ERR_BAD_ARG, "Percent given should be between 0 and 1");
+    return decode_oneshot(signal, format, n, input_rate, s, sync, reinterpret_cast<float *>(out), cap, nout, cb, user, contrast,
+                          percent, info);
+}
+
+namespace {
+
+// rows on the host -> device, image-stage kernels, results back (stage entry points; one call, no retained state)
+int image_stage_host(const float *signal, uint64_t n, int contrast, float percent, const float *bounds, apt_image_info *info,
+                     uint8_t *out, float *mean_a, float *mean_b, float *variance) {
+    if (!signal || n == 0) return fail(APT_ERR_BAD_ARG, "empty signal");   // get_min of an empty vector is an error, dsp.rs:21-25
+    APT_TRY(require_device());
+    const uint64_t rows = n / kPxPerRow;
+    const bool whole = rows * kPxPerRow == n && rows > 0;
+    if (!whole && (contrast == APT_CONTRAST_TELEMETRY || mean_a)) return fail(APT_ERR_BAD_ARG, "not a whole number of 2080-px rows");
+    DevBuf dx, dctl, dtel, dout, dbounds;
+    APT_TRY(dx.alloc(n * sizeof(float)));
+    APT_TRY(dctl.alloc(sizeof(PostCtl)));
+    APT_TRY(dtel.alloc(3 * std::max<uint64_t>(rows, 1) * sizeof(float)));
+    if (out) APT_TRY(dout.alloc(n));
+    APT_CUDA(cudaMemcpy(dx.p, signal, n * sizeof(float), cudaMemcpyHostToDevice));
+    if (bounds) {
+        APT_TRY(dbounds.alloc(2 * sizeof(float)));
+        APT_CUDA(cudaMemcpy(dbounds.p, bounds, 2 * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    const LaunchCtx c{nullptr, 148};
+    // a partial last row cannot occur in an image; min/max, percent and the map treat the signal as one row of n pixels then
+    const u32 nrows = whole ? static_cast<u32>(rows) : 1u;
+    const u32 px = whole ? kPxPerRow : static_cast<u32>(n);
+    if (!whole && n >= (1ull << 32)) return fail(APT_ERR_BAD_ARG, "signal too long");
+    float *tel = dtel.as<float>();
+    APT_TRY(launch_image_stage(c, dx.as<float>(), nullptr, nrows, nrows, px, contrast, percent, dctl.as<PostCtl>(), tel,
+                               tel + std::max<uint64_t>(rows, 1), tel + 2 * std::max<uint64_t>(rows, 1), bounds ? dbounds.as<float>() : nullptr,
+                               out ? dout.as<unsigned char>() : nullptr, out == nullptr));
+    APT_CUDA(cudaDeviceSynchronize());
+    if (!bounds) {
+        PostCtl pc;
+        APT_CUDA(cudaMemcpy(&pc, dctl.p, offsetof(PostCtl, buckets), cudaMemcpyDeviceToHost));
+        if (pc.status == 3) return fail(APT_ERR_TOO_SHORT, "Recording too short for telemetry decoding");
+        if (pc.status != 0) return fail(APT_ERR_BAD_ARG, "image stage failed (status %u)", pc.status);
+        if (info) {
+            info->low = pc.low;
+            info->high = pc.high;
+            info->rows = whole ? rows : 0;
+            info->telemetry_row = pc.telemetry_row;
+            memcpy(info->wedges_a, pc.wedges_a, sizeof(info->wedges_a));
+            memcpy(info->wedges_b, pc.wedges_b, sizeof(info->wedges_b));
+        }
+    }
+    if (out) APT_CUDA(cudaMemcpy(out, dout.p, n, cudaMemcpyDeviceToHost));
+    if (mean_a) APT_CUDA(cudaMemcpy(mean_a, tel, rows * sizeof(float), cudaMemcpyDeviceToHost));
+    if (mean_b) APT_CUDA(cudaMemcpy(mean_b, tel + rows, rows * sizeof(float), cudaMemcpyDeviceToHost));
+    if (variance) APT_CUDA(cudaMemcpy(variance, tel + 2 * rows, rows * sizeof(float), cudaMemcpyDeviceToHost));
+    return APT_OK;
+}
+
+}  // namespace
+
+extern "C" int apt_map_signal_u8(const float *signal, uint64_t n, float low, float high, uint8_t *out) {
+    if (n == 0) return APT_OK;
+    if (!out) return fail(APT_ERR_BAD_ARG, "null argument");
+    const float b[2] = {low, high};
+    return image_stage_host(signal, n, APT_CONTRAST_MINMAX, 0.f, b, nullptr, out, nullptr, nullptr, nullptr);
+}
+
+extern "C" int apt_contrast_bounds(const float *signal, uint64_t n, int contrast, float percent, apt_image_info *info) {
+    if (!info) return fail(APT_ERR_BAD_ARG, "null argument");
+    if (contrast < 0 || contrast > APT_CONTRAST_TELEMETRY) return fail(APT_ERR_BAD_ARG, "unknown contrast mode %d", contrast);
+    if (contrast == APT_CONTRAST_PERCENT && !(percent >= 0.f && percent <= 1.f))
+        return fail(APT_ERR_BAD_ARG, "Percent given should be between 0 and 1");
+    memset(info, 0, sizeof(*info));
+    return image_stage_host(signal, n, contrast, percent, nullptr, info, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int apt_telemetry_rows(const float *signal, uint64_t n, float *mean_a, float *mean_b, float *variance) {
+    if (!mean_a || !mean_b || !variance) return fail(APT_ERR_BAD_ARG, "null argument");
+    return image_stage_host(signal, n, APT_CONTRAST_MINMAX, 0.f, nullptr, nullptr, nullptr, mean_a, mean_b, variance);
 }
 
 // ============================================================================= introspection
@@ -978,6 +1166,7 @@ extern "C" int apt_decode_batch(const void *const *signals, int format, const ui
         nouts[i] = 0;
         if (statuses) statuses[i] = APT_ERR_CUDA;      // overwritten by the job's own status; never left "ok" by default
     }
+    static const bool use_cache = getenv("APTB200_NO_CACHE") == nullptr;
     std::vector<int> local_status(count, APT_ERR_CUDA);
     std::vector<std::string> messages(ndevices);
     std::vector<int> fatal(ndevices, APT_OK);
@@ -987,7 +1176,6 @@ extern "C" int apt_decode_batch(const void *const *signals, int format, const ui
         bind_thread_to_device(device);
         std::vector<apt_decoder *> decs;
         std::vector<int> job_of;
-        std::unique_ptr<HostStager> stager;
         int next = g;                                  // recording i -> device i % G   
         int in_flight = 0;
         auto reap = [&](size_t k) {
@@ -1011,20 +1199,26 @@ extern "C" int apt_decode_batch(const void *const *signals, int format, const ui
                 if (job_of[k] < 0) { free_k = k; break; }
             if (next < count && (free_k < decs.size() || static_cast<int>(decs.size()) < streams_per_device)) {
                 if (free_k == decs.size()) {
-                    apt_decoder *d = nullptr;
-                    const int st = apt_decoder_create(device, input_rate, s, max_len, &d);
+                    apt_decoder *d = cache_take(device, input_rate, *s, max_len);     // parked by an earlier call
+                    const int st = d ? APT_OK : apt_decoder_create(device, input_rate, s, max_len, &d);
                     if (st != APT_OK) {
                         if (decs.empty()) { fail_rest(st); continue; }
                         streams_per_device = static_cast<int>(decs.size());   // out of memory: make do with what exists
                         continue;
                     }
-                    if (!stager) {
-                        int threads = 8;
-                        if (const char *e = getenv("APTB200_COPY_THREADS")) threads = std::max(1, atoi(e));
-                        stager.reset(new (std::nothrow) HostStager(device, 16u << 20, 3, threads));
-                        if (stager && !stager->ok()) stager.reset();
+                    // one stager (ring + copy threads) serves all decoders of this feeder: the first decoder's own
+                    if (decs.empty()) {
+                        if (!d->own_stager) {
+                            int threads = 8;
+                            if (const char *e = getenv("APTB200_COPY_THREADS")) threads = std::max(1, atoi(e));
+                            d->own_stager.reset(new (std::nothrow) HostStager(device, 16u << 20, 3, threads));
+                            if (d->own_stager && !d->own_stager->ok()) d->own_stager.reset();
+                        }
+                        d->stager = d->own_stager.get();
+                    } else {
+                        d->stager = decs[0]->stager;
                     }
-                    d->stager = stager.get();
+                    d->image_contrast = -1;
                     decs.push_back(d);
                     job_of.push_back(-1);
                 }
@@ -1051,8 +1245,9 @@ extern "C" int apt_decode_batch(const void *const *signals, int format, const ui
             }
         }
         for (auto *d : decs) {
-            d->stager = nullptr;
-            apt_decoder_destroy(d);
+            d->stager = d->own_stager.get();           // nullptr unless it owns one: never keep a pointer into another decoder
+            if (use_cache) cache_put_multi(device, input_rate, *s, d);
+            else apt_decoder_destroy(d);
         }
     };
 

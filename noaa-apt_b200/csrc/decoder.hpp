@@ -109,6 +109,15 @@ struct apt_decoder {
     uint64_t job_d2h_floats = 0;   // rows copied back by the job (an upper bound when syncing: n_rows is not known yet)
     aptb200::SyncResult *h_res = nullptr;   // pinned
 
+    // image mode (kernels_post.cuh): the job's output is the u8 image
+    int image_contrast = -1;       // < 0: f32 rows
+    float image_percent = 0.98f;
+    aptb200::PostCtl *d_post = nullptr, *h_post = nullptr;   // device block; pinned copy of its head for the host
+    float *d_tel = nullptr;        // 3 * max_rows floats: telemetry band means and variance per row
+    unsigned char *d_out8 = nullptr;
+    bool job_image = false;
+    apt_image_info last_image{};
+
     // job in flight
     bool in_flight = false;
     bool job_host = false, job_sync = false;

@@ -134,12 +134,15 @@ void CopyPool::copy(void *dst, const void *src, size_t bytes) {
 
 HostStager::HostStager(int device, size_t chunk_bytes, int ring, int threads)
     : device_(device), chunk_(chunk_bytes), pool_(threads, device) {
+    if (const char *e = getenv("APTB200_COPY_CHUNK_MB")) chunk_ = std::max<size_t>(1, static_cast<size_t>(atoi(e))) << 20;
+    if (const char *e = getenv("APTB200_COPY_RING")) ring = std::max(2, atoi(e));
     ring_.assign(ring, nullptr);
     ev_.assign(ring, nullptr);
     used_.assign(ring, false);
     ok_ = true;
     for (int i = 0; i < ring; ++i) {
-        if (cudaHostAlloc(reinterpret_cast<void **>(&ring_[i]), chunk_, cudaHostAllocDefault) != cudaSuccess ||
+        static const bool wc = getenv("APTB200_COPY_WC") != nullptr;    // write-combined staging: experiment switch
+        if (cudaHostAlloc(reinterpret_cast<void **>(&ring_[i]), chunk_, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess ||
             cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming) != cudaSuccess) {
             cudaGetLastError();
             ok_ = false;
@@ -157,17 +160,26 @@ HostStager::~HostStager() {
 }
 
 cudaError_t HostStager::upload(void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+    static const bool trace = getenv("APTB200_TRACE_HOST") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    double t_wait = 0, t_copy = 0;
     size_t off = 0;
     size_t c = 0;
     const size_t nr = ring_.size();
     while (off < bytes) {
         const size_t nb = std::min(chunk_, bytes - off);
         const size_t r = c % nr;
+        const auto t0 = std::chrono::steady_clock::now();
         if (used_[r]) {
             const cudaError_t e = cudaEventSynchronize(ev_[r]);   // the DMA that last read this buffer has finished
             if (e != cudaSuccess) return e;
         }
+        const auto t1 = std::chrono::steady_clock::now();
         pool_.copy(ring_[r], static_cast<const char *>(src) + off, nb);
+        if (trace) {
+            t_wait += std::chrono::duration<double>(t1 - t0).count();
+            t_copy += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+        }
         cudaError_t e = cudaMemcpyAsync(static_cast<char *>(dst) + off, ring_[r], nb, cudaMemcpyHostToDevice, stream);
         if (e != cudaSuccess) return e;
         e = cudaEventRecord(ev_[r], stream);
@@ -176,6 +188,10 @@ cudaError_t HostStager::upload(void *dst, const void *src, size_t bytes, cudaStr
         off += nb;
         ++c;
     }
+    if (trace)
+        fprintf(stderr, "[aptb200 host] upload %.1f MB in %zu chunks: %.2f ms (ring waits %.2f ms, memcpy %.2f ms = %.1f GB/s, %d threads)\n",
+                bytes / 1e6, c, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() * 1e3, t_wait * 1e3,
+                t_copy * 1e3, bytes / t_copy / 1e9, pool_.threads());
     return cudaSuccess;
 }
 

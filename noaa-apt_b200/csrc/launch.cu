@@ -13,6 +13,7 @@
 #include "kernels_lpsync.cuh"
 #include "kernels_sync.cuh"
 #include "kernels_sync2.cuh"
+#include "kernels_post.cuh"
 #include "kernels_ut.cuh"
 
 namespace aptb200 {
@@ -377,6 +378,22 @@ int launch_gather_lp(const LaunchCtx &c, const float *e, u64 n, const u32 *posit
     else if (ntaps == 61 && dec == 5) k_gather_rows_lp<61, 5><<<grid, kGatherLpThreads, smem, c.stream>>>(e, n, positions, result, fixed_rows, row, px, lp, out);
     else return fail(APT_ERR_BAD_ARG, "no fused gather kernel for %u taps, decimation %u", ntaps, dec);
     static_assert(kGatherLpThreads * 4 >= 1040, "one pass of a half row");
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+int launch_image_stage(const LaunchCtx &c, const float *rows, const SyncResult *result, u32 fixed_rows, u32 max_rows, u32 px,
+                       int contrast, float percent, PostCtl *ctl, float *tel_a, float *tel_b, float *tel_v,
+                       const float *bounds_dev, unsigned char *out, bool stats_only) {
+    if (max_rows == 0) return APT_OK;
+    const unsigned wide = static_cast<unsigned>(c.sm_count) * 8;
+    if (!bounds_dev) {
+        APT_CUDA(cudaMemsetAsync(ctl, 0, sizeof(PostCtl), c.stream));
+        k_post_stats<<<std::min<unsigned>(max_rows, wide), 256, 0, c.stream>>>(rows, result, fixed_rows, px, ctl, tel_a, tel_b, tel_v);
+        if (contrast == 1) k_post_histogram<<<wide / 2, 256, 0, c.stream>>>(rows, result, fixed_rows, px, ctl);
+        k_post_bounds<<<1, 1024, 0, c.stream>>>(contrast, percent, result, fixed_rows, px, ctl, tel_a, tel_b, tel_v);
+    }
+    if (!stats_only) k_post_map_u8<<<wide, 256, 0, c.stream>>>(rows, result, fixed_rows, px, ctl, bounds_dev, out);
     APT_CUDA(cudaGetLastError());
     return APT_OK;
 }

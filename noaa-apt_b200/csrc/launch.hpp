@@ -44,6 +44,17 @@ struct Rec {
     u32 pos;           // correlation index
     float val;
 };
+// Control / result block of the image stage (kernels_post.cuh); zeroed at the start of a job.
+struct PostCtl {
+    u32 nmin_key, max_key;   // ~key(min) and key(max) of the image under the monotone float -> u32 map
+    u32 rows;                // image rows
+    u32 status;              // 0 ok; 1 empty image; 2 percent: no low bucket; 3 too short for telemetry; 4 frame runs off the image
+    float low, high;         // contrast bounds
+    u32 telemetry_row, pad;
+    float wedges_a[16], wedges_b[16];
+    u32 buckets[1000];       // misc::percent histogram
+};
+
 // Where the picker finds the roots: per block of `block` positions an ascending list.
 struct RootIndex {
     const u32 *list;
@@ -167,6 +178,13 @@ PickScratch pick_scratch_carve(void *base, u32 max_blocks, u32 max_positions, u3
 // aligned rows + final decimation (decode.rs:122-134, 158-159).  positions == nullptr: no-sync rows.
 int launch_gather(const LaunchCtx &c, const float *f, const u32 *positions, const SyncResult *result,
                   u32 fixed_rows, u32 max_rows, u32 row, u32 px, u32 dec, float *out);
+
+// Image stage: contrast bounds + telemetry statistics + u8 map of `rows` (f32, device), rows counted by
+// `result` (sync decode) or fixed_rows.  contrast: 0 min/max, 1 percent, 2 telemetry (aptb200.h apt_contrast); bounds_dev !=
+// nullptr: map with the two floats there instead (stage entry point).  tel_* are per-row scratch (max_rows floats each).
+int launch_image_stage(const LaunchCtx &c, const float *rows, const SyncResult *result, u32 fixed_rows, u32 max_rows, u32 px,
+                       int contrast, float percent, PostCtl *ctl, float *tel_a, float *tel_b, float *tel_v,
+                       const float *bounds_dev, unsigned char *out, bool stats_only);
 
 // Builds the geometry and the zero-padded per-group tap table of the tiled polyphase kernel for
 // (l, m, taps).  Returns false when the shape does not fit the kernel (the generic kernel is used then).
