@@ -50,7 +50,8 @@ typedef enum apt_status {
                                      even Kaiser window filters.rs:68-70, rate 0) or NULL pointers    */
     APT_ERR_NOMEM = 8,            /* host or device allocation failed                                 */
     APT_ERR_CAPACITY = 9,         /* caller's output buffer is too small (required size returned)     */
-    APT_ERR_EMPTY_RESULT = 10     /* Internal("Got zero samples after resampling...") resample.rs:46-52 */
+    APT_ERR_EMPTY_RESULT = 10,    /* Internal("Got zero samples after resampling...") resample.rs:46-52 */
+    APT_ERR_IO = 11               /* Io / WavOpen (err.rs:11-17): a WAV file cannot be opened, parsed or written       */
 } apt_status;
 
 const char *apt_strerror(int status);
@@ -157,6 +158,29 @@ void apt_cache_clear(void);
  * (wav.rs:31-40) is fused into the resampler's load, halving the host->device bytes. */
 int apt_decode_pcm16(const int16_t *pcm, uint64_t n, uint32_t input_rate, const apt_settings *s, int sync,
                      float *out, uint64_t cap, uint64_t *nout, apt_status_cb cb, void *user);
+
+/* ------------------------------------------------------ WAV files and the resample tool */
+
+/* wav::load_wav -- wav.rs:11-56 (the `hound` reader restated for what this path needs): integer PCM of 8/16/24/32 bits or
+ * 32-bit float, any number of channels; channel 0 is kept and integer samples are cast with `as f32` (raw values). */
+typedef struct apt_wav_info {
+    uint32_t sample_rate, channels, bits_per_sample, is_float;
+    uint64_t frames;
+} apt_wav_info;
+int apt_wav_info_read(const char *path, apt_wav_info *info);
+int apt_wav_load(const char *path, float *out, uint64_t cap, uint64_t *n, uint32_t *sample_rate);
+/* The 16-bit samples as they are (for apt_decode_pcm16 / APT_PCM16: half the PCIe bytes, cast on the device). */
+int apt_wav_load_pcm16(const char *path, int16_t *out, uint64_t cap, uint64_t *n, uint32_t *sample_rate);
+/* 16-bit mono PCM file, what resample.rs:53-66 writes. */
+int apt_wav_write_i16(const char *path, const int16_t *samples, uint64_t n, uint32_t sample_rate);
+/* wav::write_wav's conversion for 16-bit files -- wav.rs:71-85: (sample / max * 32767.0) as i16 with max = dsp::get_max,
+ * on the device; bit-identical to the reference given the same signal. */
+int apt_quantize_i16(const float *signal, uint64_t n, int16_t *out);
+/* resample::resample -- resample.rs:17-71: load WAV, dsp::resample (Lowpass, atten dB, delta_w in pi rad/sample) on the
+ * GPU, normalise + quantise on the GPU, write a 16-bit WAV.  (The modification-time copy of resample.rs:30,68 is file
+ * plumbing and stays with the caller.)  *nout receives the number of samples written. */
+int apt_resample_wav(const char *input_path, const char *output_path, uint32_t output_rate, float atten, float delta_w_pi,
+                     uint64_t *nout);
 
 /* ------------------------------------------ image stage (after decode, on the device) */
 
@@ -294,6 +318,16 @@ typedef struct apt_ut_info {
 } apt_ut_info;
 int apt_ut_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_ut_info *info, float *stream,
                 size_t cap_stream);
+
+/* Geometry and phase table of the phase-major resampler (noaa-apt_b200/csrc/kernels_ph.cuh), the kernel that serves
+ * fast_resampling + demodulate for large interpolation factors (11025 / 22050 / 44100 Hz -> 12 480 Hz: L = 832 / 416 / 208).
+ * Host logic only.  usable == 0: the shape does not fit.  Output k = l*q + r is
+ *     sum_{j < jpad} table[r*jpad + j] * signal[m*q + xs[r] + j]        (samples beyond the end count as zero). */
+typedef struct apt_ph_info {
+    uint32_t usable, l, m, j, jpad, pitch, row_len, smem_bytes;
+} apt_ph_info;
+int apt_ph_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_ph_info *info, float *table, size_t cap_table,
+                uint16_t *xs, size_t cap_xs);
 
 /* ------------------------------------------------------------------ batch */
 

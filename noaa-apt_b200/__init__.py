@@ -10,7 +10,7 @@ Mirrors the module layout of martinber/noaa-apt's hot path:
 Every compute call goes through the C ABI of libaptb200.so (include/aptb200.h) into hand-written
 sm_100a CUDA kernels.  There is no CPU path: importing works anywhere, computing needs a GPU.
 """
-from . import _lib, config, context, dsp, err, filters, frequency, image  # noqa: F401
+from . import _lib, config, context, dsp, err, filters, frequency, image, wav  # noqa: F401
 from . import decode as _decode_mod
 from .config import Settings
 from .context import Context
@@ -19,7 +19,7 @@ from .decode import (CARRIER_FREQ, FINAL_RATE, PX_PER_ROW, Decoder, decode, deco
 from .frequency import Freq, Rate
 
 __all__ = ["decode", "decode_batch", "decode_len_bound", "find_sync", "generate_sync_frame", "Decoder",
-           "Settings", "Context", "Freq", "Rate", "dsp", "filters", "err", "config", "frequency", "image",
+           "Settings", "Context", "Freq", "Rate", "dsp", "filters", "err", "config", "frequency", "image", "wav",
            "FINAL_RATE", "PX_PER_ROW", "CARRIER_FREQ"]
 
 

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libaptb200.so")
+LIB_PATH = os.environ.get("APTB200_LIB") or os.path.join(HERE, "libaptb200.so")   # APTB200_LIB: an experimental build
 
 OK = 0
 ERR_RESAMPLE_TO_ZERO = 1
@@ -20,6 +20,7 @@ ERR_BAD_ARG = 7
 ERR_NOMEM = 8
 ERR_CAPACITY = 9
 ERR_EMPTY_RESULT = 10
+ERR_IO = 11
 
 FILTER_NONE, FILTER_LOWPASS, FILTER_LOWPASS_DC = 0, 1, 2
 F32, PCM16 = 0, 1
@@ -63,6 +64,15 @@ class CImageInfo(C.Structure):
 
 CONTRAST_MINMAX, CONTRAST_PERCENT, CONTRAST_TELEMETRY = 0, 1, 2
 
+class CWavInfo(C.Structure):
+    _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits_per_sample", C.c_uint32), ("is_float", C.c_uint32),
+                ("frames", C.c_uint64)]
+
+
+class CPhInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("usable", "l", "m", "j", "jpad", "pitch", "row_len", "smem_bytes")]
+
+
 STATUS_CB = C.CFUNCTYPE(None, C.c_float, C.c_char_p, C.c_void_p)
 
 # name -> (restype, argtypes); every symbol include/aptb200.h declares.
@@ -94,6 +104,12 @@ SIGNATURES = {
                              C.c_void_p, C.c_uint64, _u64p, STATUS_CB, C.c_void_p]),
     "apt_decode_pcm16": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(CSettings), C.c_int,
                                    C.c_void_p, C.c_uint64, _u64p, STATUS_CB, C.c_void_p]),
+    "apt_wav_info_read": (C.c_int, [C.c_char_p, C.POINTER(CWavInfo)]),
+    "apt_wav_load": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64, _u64p, C.POINTER(C.c_uint32)]),
+    "apt_wav_load_pcm16": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64, _u64p, C.POINTER(C.c_uint32)]),
+    "apt_wav_write_i16": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint32]),
+    "apt_quantize_i16": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "apt_resample_wav": (C.c_int, [C.c_char_p, C.c_char_p, C.c_uint32, C.c_float, C.c_float, _u64p]),
     "apt_decode_image_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint32, C.POINTER(CSettings), C.c_int, C.c_int,
                                       C.c_float, C.c_void_p, C.c_uint64, _u64p, C.POINTER(CImageInfo), STATUS_CB, C.c_void_p]),
     "apt_map_signal_u8": (C.c_int, [C.c_void_p, C.c_uint64, C.c_float, C.c_float, C.c_void_p]),
@@ -126,6 +142,8 @@ SIGNATURES = {
     "apt_device_free": (None, [C.c_int, C.c_void_p]),
     "apt_memcpy_h2d": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "apt_memcpy_d2h": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "apt_ph_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(CPhInfo), C.c_void_p, C.c_size_t,
+                              C.c_void_p, C.c_size_t]),
     "apt_ut_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(CUtInfo), C.c_void_p, C.c_size_t]),
     "apt_tile_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(CTileInfo), C.c_void_p,
                                 C.c_size_t, C.c_void_p, C.c_size_t]),

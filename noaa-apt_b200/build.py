@@ -39,15 +39,16 @@ def up_to_date():
     return all(os.path.getmtime(f) <= t for f in _deps())
 
 
-def build_library(force=False, verbose=False, extra_flags=()):
-    if not force and up_to_date():
+def build_library(force=False, verbose=False, extra_flags=(), out=None):
+    """out: build an experimental variant next to the product library (select it with APTB200_LIB=<path>)."""
+    if out is None and not force and up_to_date():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", out or LIB] + sources()
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -63,7 +63,7 @@ int free_decoder_buffers(apt_decoder *d) {
     for (void *p : {(void *)d->d_h, (void *)d->d_lp, (void *)d->d_one, (void *)d->d_guard, d->d_in, (void *)d->d_r,
                     (void *)d->d_e, (void *)d->d_f, (void *)d->d_corr, (void *)d->d_aligned, (void *)d->d_root_list,
                     (void *)d->d_root_count, (void *)d->d_pos, (void *)d->d_res, (void *)d->d_out, d->d_pick, (void *)d->d_tile_taps, (void *)d->d_tile_xs, (void *)d->d_conv,
-                    (void *)d->d_ctl, (void *)d->d_desc, (void *)d->d_pool, (void *)d->d_roots2, (void *)d->d_tile_base, (void *)d->d_by_id})
+                    (void *)d->d_ph_table, (void *)d->d_ph_xs, (void *)d->d_ctl, (void *)d->d_desc, (void *)d->d_pool, (void *)d->d_roots2, (void *)d->d_tile_base, (void *)d->d_by_id})
         if (p) cudaFree(p);
     if (d->h_res) cudaFreeHost(d->h_res);
     if (d->h_out) cudaFreeHost(d->h_out);
@@ -142,6 +142,7 @@ extern "C" const char *apt_strerror(int status) {
     case APT_ERR_NOMEM: return "out of memory";
     case APT_ERR_CAPACITY: return "output buffer too small";
     case APT_ERR_EMPTY_RESULT: return "Got zero samples after resampling, audio file too short or output sampling frequency too low";
+    case APT_ERR_IO: return "WAV file cannot be opened, parsed or written";
     default: return "unknown status";
     }
 }
@@ -287,8 +288,22 @@ extern "C" int apt_resample_with_filter(const float *signal, uint64_t n, uint32_
                                            1.f, dy.as<float>()));
             APT_CUDA(cudaDeviceSynchronize());
         } else {
-            APT_TRY(launch_polyphase(c, dx.p, APT_F32, n, dh.as<float>(), rp.r.l, rp.r.m, off2, 0, rp.nout, false, 0.f, 1.f,
-                                     dy.as<float>()));
+            PhPlan pp{};
+            std::vector<float> ptab;
+            std::vector<unsigned short> pxs;
+            if (!getenv("APTB200_GENERIC_RESAMPLER") && make_ph_plan(rp.r.l, rp.r.m, rp.taps, pp, ptab, pxs)) {
+                DevBuf dt, dg;
+                APT_TRY(dt.alloc(ptab.size() * sizeof(float)));
+                APT_TRY(dg.alloc(pxs.size() * sizeof(unsigned short)));
+                APT_CUDA(cudaMemcpy(dt.p, ptab.data(), ptab.size() * sizeof(float), cudaMemcpyHostToDevice));
+                APT_CUDA(cudaMemcpy(dg.p, pxs.data(), pxs.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+                APT_TRY(launch_polyphase_ph(c, dx.p, APT_F32, n, dt.as<float>(), dg.as<unsigned short>(), pp, rp.nout, 0, 0, false, 0.f,
+                                            1.f, dy.as<float>()));
+                APT_CUDA(cudaDeviceSynchronize());
+            } else {
+                APT_TRY(launch_polyphase(c, dx.p, APT_F32, n, dh.as<float>(), rp.r.l, rp.r.m, off2, 0, rp.nout, false, 0.f, 1.f,
+                                         dy.as<float>()));
+            }
         }
     } else {
         APT_TRY(launch_fir_decimate(c, dx.p, APT_F32, dh.as<float>(), static_cast<u32>(rp.taps.size()), rp.r.m,
@@ -459,6 +474,12 @@ extern "C" int apt_decoder_create(int device, uint32_t input_rate, const apt_set
     APT_CUDA(cudaMemcpy(d->d_lp, p.lp.data(), p.lp.size() * sizeof(float), cudaMemcpyHostToDevice));
     APT_CUDA(cudaMalloc(&d->d_one, sizeof(float)));
     APT_CUDA(cudaMemcpy(d->d_one, &one, sizeof(float), cudaMemcpyHostToDevice));
+    if (p.ph) {
+        APT_CUDA(cudaMalloc(&d->d_ph_table, p.ph_table.size() * sizeof(float)));
+        APT_CUDA(cudaMemcpy(d->d_ph_table, p.ph_table.data(), p.ph_table.size() * sizeof(float), cudaMemcpyHostToDevice));
+        APT_CUDA(cudaMalloc(&d->d_ph_xs, p.ph_xs.size() * sizeof(unsigned short)));
+        APT_CUDA(cudaMemcpy(d->d_ph_xs, p.ph_xs.data(), p.ph_xs.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    }
     if (p.tiled) {
         APT_CUDA(cudaMalloc(&d->d_tile_taps, p.tile_taps.size() * sizeof(float)));
         APT_CUDA(cudaMemcpy(d->d_tile_taps, p.tile_taps.data(), p.tile_taps.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1096,6 +1117,47 @@ extern "C" int apt_telemetry_rows(const float *signal, uint64_t n, float *mean_a
     return image_stage_host(signal, n, APT_CONTRAST_MINMAX, 0.f, nullptr, nullptr, nullptr, mean_a, mean_b, variance);
 }
 
+// ======================================================================= resample tool (WAV -> WAV)
+
+extern "C" int apt_quantize_i16(const float *signal, uint64_t n, int16_t *out) {
+    if (n == 0 || !signal) return fail(APT_ERR_BAD_ARG, "Can't get maximum of a zero length vector");   // dsp.rs:21-25
+    if (!out) return fail(APT_ERR_BAD_ARG, "null argument");
+    APT_TRY(require_device());
+    DevBuf dx, dctl, dout;
+    APT_TRY(dx.alloc(n * sizeof(float)));
+    APT_TRY(dctl.alloc(sizeof(PostCtl)));
+    APT_TRY(dout.alloc(n * sizeof(int16_t)));
+    APT_CUDA(cudaMemcpy(dx.p, signal, n * sizeof(float), cudaMemcpyHostToDevice));
+    APT_TRY(launch_quantize_i16(LaunchCtx{nullptr, 148}, dx.as<float>(), n, dctl.as<PostCtl>(), dout.as<short>()));
+    APT_CUDA(cudaMemcpy(out, dout.p, n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    return APT_OK;
+}
+
+extern "C" int apt_resample_wav(const char *input_path, const char *output_path, uint32_t output_rate, float atten,
+                                float delta_w_pi, uint64_t *nout) {
+    if (nout) *nout = 0;
+    apt_wav_info wi{};
+    APT_TRY(apt_wav_info_read(input_path, &wi));
+    std::vector<float> x(wi.frames);
+    uint64_t n = 0;
+    uint32_t rate = 0;
+    APT_TRY(apt_wav_load(input_path, x.data(), x.size(), &n, &rate));
+    if (rate == 0) return fail(APT_ERR_BAD_ARG, "invalid input rate");
+    const float cut_hz = output_rate > rate ? static_cast<float>(rate) / 2.f : static_cast<float>(output_rate) / 2.f;   // dsp.rs:140-149
+    apt_filter f{APT_FILTER_LOWPASS, Freq::hz(cut_hz, rate).get_pi_rad(), atten, delta_w_pi};
+    uint64_t ny = 0;
+    APT_TRY(apt_resample_len(n, rate, output_rate, &f, &ny));
+    if (ny == 0)   // resample.rs:46-52
+        return fail(APT_ERR_EMPTY_RESULT, "Got zero samples after resampling, audio file too short or output sampling frequency too low");
+    std::vector<float> y(ny);
+    APT_TRY(apt_resample_with_filter(x.data(), n, rate, output_rate, &f, y.data(), y.size(), &ny));
+    std::vector<int16_t> q(ny);
+    APT_TRY(apt_quantize_i16(y.data(), ny, q.data()));
+    APT_TRY(apt_wav_write_i16(output_path, q.data(), ny, output_rate));
+    if (nout) *nout = ny;
+    return APT_OK;
+}
+
 // ============================================================================= introspection
 
 extern "C" int apt_tile_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_tile_info *info,
@@ -1131,6 +1193,20 @@ extern "C" int apt_ut_plan(uint32_t l, uint32_t m, const float *taps, size_t nta
         info->ce[p] = up.ce[p];
     }
     if (stream) memcpy(stream, st.data(), std::min(cap_stream, st.size()) * sizeof(float));
+    return APT_OK;
+}
+
+extern "C" int apt_ph_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_ph_info *info, float *table,
+                           size_t cap_table, uint16_t *xs, size_t cap_xs) {
+    if (!taps || !info) return fail(APT_ERR_BAD_ARG, "null argument");
+    std::vector<float> h(taps, taps + ntaps), tb;
+    std::vector<unsigned short> x;
+    PhPlan pp{};
+    memset(info, 0, sizeof(*info));
+    if (!make_ph_plan(l, m, h, pp, tb, x)) return APT_OK;
+    *info = apt_ph_info{1, pp.l, pp.m, pp.j, pp.jpad, pp.pitch, pp.row_len, pp.smem_bytes};
+    if (table) memcpy(table, tb.data(), std::min(cap_table, tb.size()) * sizeof(float));
+    if (xs) memcpy(xs, x.data(), std::min(cap_xs, x.size()) * sizeof(uint16_t));
     return APT_OK;
 }
 

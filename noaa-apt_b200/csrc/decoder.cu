@@ -56,6 +56,8 @@ int make_plan(uint32_t input_rate, const apt_settings &s, Plan &p) {
               make_tile_plan(p.first.l, p.first.m, p.h, p.tile, p.tile_taps, p.tile_xs);
     p.ut = p.first_polyphase && !getenv("APTB200_GENERIC_RESAMPLER") &&
            make_ut_plan(p.first.l, p.first.m, p.h, p.utp, p.ut_stream);
+    p.ph = p.first_polyphase && !p.ut && !p.tiled && !getenv("APTB200_GENERIC_RESAMPLER") &&
+           make_ph_plan(p.first.l, p.first.m, p.h, p.php, p.ph_table, p.ph_xs);
 
     // decode.rs:95-100
     const float cut = static_cast<float>(kFinalRate) / static_cast<float>(s.work_rate);
@@ -207,8 +209,9 @@ int materialise_stages(apt_decoder *d) {
     return APT_OK;
 }
 
-// one of the two TMA-staged resamplers serves this decoder's first stage
+// one of the two TMA-staged resamplers serves this decoder's first stage (they take f32 samples only)
 static bool fast_front(const apt_decoder *d) { return d->plan.ut || (d->plan.tiled && d->d_tile_taps); }
+static bool ph_front(const apt_decoder *d) { return d->plan.ph && d->d_ph_table; }
 
 // fast_resampling + demodulate of outputs produced from a device-resident (or staged) chunk.
 // `in` is the address sample 0 of the recording would have (a biased pointer for chunk buffers).
@@ -228,6 +231,9 @@ static int launch_front_polyphase(apt_decoder *d, const void *in, int format, ui
         return launch_polyphase_tiled(c, fin, n, d->d_tile_taps, d->d_tile_xs, p.tile, nwork, tile_begin, tile_end, true,
                                       p.cosphi2, p.sinphi, d->d_e);
     }
+    if (ph_front(d))   // large L: phase-major kernel, f32 or PCM16 samples (the cast is part of its row staging)
+        return launch_polyphase_ph(c, in, format, n, d->d_ph_table, d->d_ph_xs, p.php, nwork, tile_begin, tile_end, true, p.cosphi2,
+                                   p.sinphi, d->d_e);
     return launch_polyphase(c, in, format, n, d->d_h, p.first.l, p.first.m, p.off2, k_begin, k_end ? k_end : nwork, true,
                             p.cosphi2, p.sinphi, d->d_e);
 }
@@ -239,7 +245,7 @@ static int enqueue_front_chunked(apt_decoder *d, const void *host, int format, u
     const LaunchCtx c{d->stream, d->sm_count};
     const size_t sb = format == APT_PCM16 ? 2 : 4;
     const uint64_t cap = d->chunk_samples;
-    const bool tiled = fast_front(d);
+    const bool tiled = fast_front(d) || ph_front(d);
     const uint64_t l = p.first.l, m = p.first.m;
     uint64_t units, per_chunk;            // tiles / blocks or outputs
     // a unit (tile of the warp-specialised kernel, block of the uniform-tap kernel) reads unit_in new samples,
@@ -250,6 +256,11 @@ static int enqueue_front_chunked(apt_decoder *d, const void *host, int format, u
         unit_out = static_cast<uint64_t>(p.utp.rb) * l;
         before = p.utp.back;
         after = p.utp.slot_floats - p.utp.back;           // a block's span beyond its first row's first sample
+    } else if (ph_front(d)) {
+        unit_in = static_cast<uint64_t>(kPhTilePeriods) * m;              // a tile = 32 periods of m samples
+        unit_out = static_cast<uint64_t>(kPhTilePeriods) * l;
+        before = m + 4;                                                   // the period in front of the tile (+4 alignment)
+        after = static_cast<uint64_t>(kPhTilePeriods - 1) * m + p.php.row_len;
     } else if (tiled) {
         unit_in = static_cast<uint64_t>(p.tile.qt) * p.tile.p_in;
         unit_out = static_cast<uint64_t>(p.tile.qt) * p.tile.p_out;
@@ -296,7 +307,7 @@ static int enqueue_front_chunked(apt_decoder *d, const void *host, int format, u
         // compute stream: (cast,) resample + envelope of this chunk's outputs
         const void *in_biased = stage[b] - xa * sb;
         float *conv_biased = nullptr;
-        if (format == APT_PCM16 && tiled) {
+        if (format == APT_PCM16 && fast_front(d)) {
             APT_TRY(launch_pcm16_to_f32(c, reinterpret_cast<const int16_t *>(stage[b]), xb - xa, d->d_conv));
             d->launches++;
             conv_biased = d->d_conv - xa;

@@ -42,6 +42,10 @@ struct Plan {
     TilePlan tile{};
     std::vector<float> tile_taps;
     std::vector<u32> tile_xs;
+    bool ph = false;               // the phase-major resampler (large L: 11025 / 22050 / 44100 Hz) fits
+    PhPlan php{};
+    std::vector<float> ph_table;
+    std::vector<unsigned short> ph_xs;
     bool ut = false;               // the uniform-tap resampler (taps as a kernel parameter) fits: preferred
     UtPlan utp{};
     std::vector<float> ut_stream;
@@ -65,6 +69,8 @@ struct apt_decoder {
     uint32_t max_blocks = 0, max_positions = 0;
 
     float *d_h = nullptr, *d_lp = nullptr, *d_one = nullptr;
+    float *d_ph_table = nullptr;
+    unsigned short *d_ph_xs = nullptr;
     float *d_tile_taps = nullptr;
     aptb200::u32 *d_tile_xs = nullptr;
     int8_t *d_guard = nullptr;

@@ -49,7 +49,7 @@ k_post_stats(const float *__restrict__ rows, const SyncResult *__restrict__ resu
             kmin = min(kmin, k);
             kmax = max(kmax, k);
         }
-        if (threadIdx.x < 2 && px >= 2078) {
+        if (threadIdx.x < 2 && px >= 2078 && mean_a != nullptr) {
             const float *band = line + (threadIdx.x == 0 ? 994 : 2034);
             float sum = 0.f;
             for (int i = 0; i < 44; ++i) sum = __fadd_rn(sum, band[i]);
@@ -248,6 +248,22 @@ k_post_map_u8(const float *__restrict__ rows, const SyncResult *__restrict__ res
     } else {
         for (u64 i = static_cast<u64>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<u64>(gridDim.x) * blockDim.x)
             out[i] = map_u8(rows[i], low, range);
+    }
+}
+
+// wav.rs:71-85 for 16-bit files: (sample / max * 32767.0) as i16 -- `as` truncates toward zero, saturates, NaN -> 0.
+// The maximum arrives as the float key that k_post_stats leaves in ctl->max_key.
+__global__ void __launch_bounds__(256)
+k_quantize_i16(const float *__restrict__ x, u64 n, const PostCtl *__restrict__ ctl, short *__restrict__ out) {
+    const float mx = key_float(ctl->max_key);
+    for (u64 i = static_cast<u64>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<u64>(gridDim.x) * blockDim.x) {
+        const float v = __fmul_rn(__fdiv_rn(x[i], mx), 32767.f);
+        short q;
+        if (v != v) q = 0;
+        else if (v >= 32767.f) q = 32767;
+        else if (v <= -32768.f) q = -32768;
+        else q = static_cast<short>(static_cast<int>(v));           // cvt.rzi
+        out[i] = q;
     }
 }
 

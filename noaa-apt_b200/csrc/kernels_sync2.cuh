@@ -354,6 +354,8 @@ k_lowpass_records(const float *__restrict__ e, u64 n, u64 ncorr, const __grid_co
         }
         __syncwarp();
         if (fits) {
+            // every lane writes its own records (a warp-cooperative, coalesced variant with a shuffle search per record
+            // measured 10 us slower: the lists are short and the shuffles are not free)
 #pragma unroll
             for (int rd = 0; rd < RD; ++rd) {
                 const float *crow = s + (32 * rd + lane) * PITCH;

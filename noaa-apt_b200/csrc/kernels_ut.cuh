@@ -81,10 +81,13 @@ __device__ __forceinline__ void ut_load_chunk(const float *p, float (&s)[CH]) {
 
 // Chunks [cb, ce) with pairs [P0, P1) of a role active.  toff: running float4 index into the tap stream (uniform);
 // per (chunk, pair) the stream holds CH/2 float4 = the tap pairs of the chunk's CH samples.
-template <int P0, int P1, int NPR, int Q, int VEC, int MAXV>
+#ifndef APTB200_UT_STEADY_UNROLL
+#define APTB200_UT_STEADY_UNROLL 1
+#endif
+template <int P0, int P1, int NPR, int Q, int VEC, int MAXV, int UNR = 1>
 __device__ __forceinline__ void ut_segment(const UtParams<MAXV> &prm, u32 cb, u32 ce, int &toff, const float *row0,
                                            u32 qstride, f32x2 (&acc)[Q][NPR]) {
-#pragma unroll 1
+#pragma unroll UNR
     for (u32 c = cb; c < ce; ++c) {
         float s[Q][CH];
 #pragma unroll
@@ -148,7 +151,7 @@ __device__ __forceinline__ void ut_role(const UtParams<MAXV> &prm, const UtGeom 
     const float *row0 = slot + g.back + lane * m;
     if (g.debug != 1) {
         ut_ramp_up<PB, NPR, Q, VEC, MAXV>(prm, toff, row0, qstride, acc, std::make_integer_sequence<int, NPR - 1>{});
-        ut_segment<0, NPR, NPR, Q, VEC, MAXV>(prm, prm.cs[PB + NPR - 1], prm.ce[PB], toff, row0, qstride, acc);
+        ut_segment<0, NPR, NPR, Q, VEC, MAXV, APTB200_UT_STEADY_UNROLL>(prm, prm.cs[PB + NPR - 1], prm.ce[PB], toff, row0, qstride, acc);
         ut_ramp_down<PB, NPR, Q, VEC, MAXV>(prm, toff, row0, qstride, acc, std::make_integer_sequence<int, NPR - 1>{});
     }
     UT_MARK(2)
@@ -203,12 +206,24 @@ __device__ __forceinline__ void ut_role(const UtParams<MAXV> &prm, const UtGeom 
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(staged_bar);
+#ifdef APTB200_UT_ROLE1_STORES
+    // experiment: the lighter role (3 of the 7 pairs) stores the whole block, the heavier one moves on to its next ticket
+    if (!LAST) return;
+    mbar_wait(staged_bar, parity);
+    UT_MARK(4)
+    constexpr u32 nvec = RB * L / 4;
+#pragma unroll
+    for (u32 vi = 0; vi < (nvec + 31) / 32; ++vi) {
+        const u32 v = lane + 32 * vi;
+        (void)role;
+#else
     mbar_wait(staged_bar, parity);
     UT_MARK(4)
     constexpr u32 nvec = RB * L / 4;                                   // RB*L is a multiple of 4
 #pragma unroll
     for (u32 vi = 0; vi < (nvec + 63) / 64; ++vi) {
         const u32 v = lane + 32 * (2 * vi + role);
+#endif
         const u64 k = k0 + 4 * v;
         if (v >= nvec || k >= nout) break;
         float4 val = *reinterpret_cast<const float4 *>(slot + 4 * v);

@@ -11,6 +11,7 @@
 #include "kernels_fast.cuh"
 #include "kernels_generic.cuh"
 #include "kernels_lpsync.cuh"
+#include "kernels_ph.cuh"
 #include "kernels_sync.cuh"
 #include "kernels_sync2.cuh"
 #include "kernels_post.cuh"
@@ -172,6 +173,34 @@ int launch_polyphase_ut(const LaunchCtx &c, const float *signal, u64 len, const 
                         : launch_ut_vec<2, false>(c, signal, len, h, up, stream, nout, blk_begin, nblk, cosphi2, sinphi, out);
     return envelope ? launch_ut_vec<1, true>(c, signal, len, h, up, stream, nout, blk_begin, nblk, cosphi2, sinphi, out)
                     : launch_ut_vec<1, false>(c, signal, len, h, up, stream, nout, blk_begin, nblk, cosphi2, sinphi, out);
+}
+
+int launch_polyphase_ph(const LaunchCtx &c, const void *signal, int format, u64 len, const float *table_dev,
+                        const unsigned short *xs_dev, const PhPlan &pp, u64 nout, u64 tile_begin, u64 tile_end, bool envelope,
+                        float cosphi2, float sinphi, float *out) {
+    if (nout == 0) return APT_OK;
+    const u64 tile_out = static_cast<u64>(kPhPeriods) * pp.l;
+    u64 ntiles = (nout + tile_out - 1) / tile_out;
+    if (tile_end != 0) ntiles = std::min(ntiles, tile_end);
+    if (tile_begin >= ntiles) return APT_OK;
+    const PhGeom g{pp.l, pp.m, pp.j, pp.pitch, pp.row_len, pp.smem_bytes};
+    const unsigned grid = static_cast<unsigned>(std::min<u64>(ntiles - tile_begin, static_cast<u64>(c.sm_count)));
+    auto launch = [&](auto kern, auto *sig) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pp.smem_bytes));
+        kern<<<grid, 32 * kPhWarps, pp.smem_bytes, c.stream>>>(sig, len, table_dev, xs_dev, g, nout, tile_begin, ntiles, envelope ? 1 : 0,
+                                                              cosphi2, 1.0f / sinphi, out);
+    };
+    const float *sf = static_cast<const float *>(signal);
+    const int16_t *si = static_cast<const int16_t *>(signal);
+    const bool pcm = format == APT_PCM16;
+    switch (pp.jpad) {
+    case 20: if (pcm) launch(k_polyphase_ph<int16_t, 20>, si); else launch(k_polyphase_ph<float, 20>, sf); break;
+    case 36: if (pcm) launch(k_polyphase_ph<int16_t, 36>, si); else launch(k_polyphase_ph<float, 36>, sf); break;
+    case 68: if (pcm) launch(k_polyphase_ph<int16_t, 68>, si); else launch(k_polyphase_ph<float, 68>, sf); break;
+    default: return fail(APT_ERR_BAD_ARG, "phase-major resampler: no instantiation for %u taps per output", pp.jpad);
+    }
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
 }
 
 int launch_fir_decimate(const LaunchCtx &c, const void *signal, int format, const float *coeff, u32 ntaps, u32 m,
@@ -394,6 +423,18 @@ int launch_image_stage(const LaunchCtx &c, const float *rows, const SyncResult *
         k_post_bounds<<<1, 1024, 0, c.stream>>>(contrast, percent, result, fixed_rows, px, ctl, tel_a, tel_b, tel_v);
     }
     if (!stats_only) k_post_map_u8<<<wide, 256, 0, c.stream>>>(rows, result, fixed_rows, px, ctl, bounds_dev, out);
+    APT_CUDA(cudaGetLastError());
+    return APT_OK;
+}
+
+int launch_quantize_i16(const LaunchCtx &c, const float *x, u64 n, PostCtl *ctl, short *out) {
+    if (n == 0) return APT_OK;
+    if (n >= (1ull << 32)) return fail(APT_ERR_BAD_ARG, "signal too long");
+    APT_CUDA(cudaMemsetAsync(ctl, 0, sizeof(PostCtl), c.stream));
+    const unsigned wide = static_cast<unsigned>(c.sm_count) * 8;
+    // the signal as one "row" of n pixels: only the maximum is used
+    k_post_stats<<<1, 256, 0, c.stream>>>(x, nullptr, 1, static_cast<u32>(n), ctl, nullptr, nullptr, nullptr);
+    k_quantize_i16<<<wide, 256, 0, c.stream>>>(x, n, ctl, out);
     APT_CUDA(cudaGetLastError());
     return APT_OK;
 }

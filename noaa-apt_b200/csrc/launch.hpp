@@ -132,6 +132,16 @@ struct UtPlan {
     u32 debug;
 };
 
+// Geometry of the phase-major resampler (kernels_ph.cuh) for large interpolation factors; built by make_ph_plan.
+constexpr u32 kPhTilePeriods = 32;   // periods (= l outputs each) per tile of the phase-major resampler
+struct PhPlan {
+    u32 l, m;
+    u32 j, jpad;       // taps per output, padded to the kernel's instantiation (20 / 36 / 68)
+    u32 pitch;         // floats per shared-memory input row
+    u32 row_len;       // samples staged per row
+    u32 smem_bytes;
+};
+
 struct LaunchCtx {
     cudaStream_t stream;
     int sm_count;
@@ -186,6 +196,9 @@ int launch_image_stage(const LaunchCtx &c, const float *rows, const SyncResult *
                        int contrast, float percent, PostCtl *ctl, float *tel_a, float *tel_b, float *tel_v,
                        const float *bounds_dev, unsigned char *out, bool stats_only);
 
+// wav.rs:71-85: normalise by the maximum and quantise to i16 (x, out: device; ctl: scratch control block).
+int launch_quantize_i16(const LaunchCtx &c, const float *x, u64 n, PostCtl *ctl, short *out);
+
 // Builds the geometry and the zero-padded per-group tap table of the tiled polyphase kernel for
 // (l, m, taps).  Returns false when the shape does not fit the kernel (the generic kernel is used then).
 bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, std::vector<float> &tile_taps,
@@ -195,6 +208,15 @@ bool make_tile_plan(u32 l, u32 m, const std::vector<float> &taps, TilePlan &tp, 
 int launch_polyphase_tiled(const LaunchCtx &c, const float *signal, u64 len, const float *tile_taps,
                            const u32 *group_xs, const TilePlan &tp, u64 nout, u64 tile_begin, u64 tile_end,
                            bool envelope, float cosphi2, float sinphi, float *out);
+
+// Phase-major resampler (+ envelope) for large L (11025 / 22050 / 44100 Hz input).  make_ph_plan returns false when the
+// shape does not fit (then the generic kernel serves it); table = [l][jpad] taps, xs = [l] window starts, both go to HBM.
+bool make_ph_plan(u32 l, u32 m, const std::vector<float> &taps, PhPlan &pp, std::vector<float> &table,
+                  std::vector<unsigned short> &xs);
+// Tiles of 32 periods (32*l outputs) [tile_begin, tile_end) (tile_end == 0: all); `signal` is the address sample 0 would have.
+int launch_polyphase_ph(const LaunchCtx &c, const void *signal, int format, u64 len, const float *table_dev,
+                        const unsigned short *xs_dev, const PhPlan &pp, u64 nout, u64 tile_begin, u64 tile_end, bool envelope,
+                        float cosphi2, float sinphi, float *out);
 
 // Uniform-tap resampler (+ envelope): taps travel as a kernel parameter.  Returns false from make_ut_plan when
 // (l, m, taps) does not fit (L other than 13/14, tap stream too long, rows too long for shared memory).

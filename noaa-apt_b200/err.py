@@ -24,6 +24,10 @@ class InvalidInput(Error):
     """Inputs on which the reference panics (empty signal, rate 0, NULL) or a too-small buffer."""
 
 
+class Io(Error):
+    """err::Error::Io / WavOpen (err.rs:11-17): a WAV file cannot be opened, parsed or written."""
+
+
 class CudaError(Error):
     """CUDA failure or no device.  There is no CPU fallback."""
 
@@ -37,6 +41,8 @@ def raise_for(code):
         raise Internal(code, msg)
     if code == _lib.ERR_RATE_OVERFLOW:
         raise RateOverflow(code, msg)
+    if code == _lib.ERR_IO:
+        raise Io(code, msg)
     if code in (_lib.ERR_CUDA, _lib.ERR_NOMEM):
         raise CudaError(code, msg)
     raise InvalidInput(code, msg)

@@ -302,3 +302,89 @@ def test_uniform_tap_plan_rejects_other_ratios(na):
     for l, m in ((832, 735), (26, 75), (208, 735)):
         info, _ = _ut_plan(na, l, m, h)
         assert not info.usable
+
+
+@pytest.mark.parametrize("in_rate,work_rate,atten,dfreq", [(11025, 12480, 30.0, 1000.0), (22050, 12480, 30.0, 1000.0),
+                                                           (44100, 12480, 30.0, 1000.0), (11025, 20800, 40.0, 500.0)])
+def test_phase_major_plan_reproduces_fast_resampling(in_rate, work_rate, atten, dfreq):
+    """Host logic of kernels_ph.cuh: y[l*q + r] = sum_j table[r][j] * x[m*q + xs[r] + j] must be fast_resampling
+    (dsp.rs:186-289) -- emulated in numpy (float64 accumulation) against the oracle."""
+    import math
+    import oracle
+    from noaa_apt_b200 import _lib
+    lib = _lib.load()
+    g = math.gcd(in_rate, work_rate)
+    l, m = work_rate // g, in_rate // g
+    cut, dw = oracle.freq_hz(4800.0, in_rate), oracle.freq_hz(dfreq, in_rate)
+    ratio = np.float32(in_rate * l) / np.float32(in_rate)
+    taps = oracle.design(oracle.FILTER_LOWPASS_DC, float(np.float32(cut) / ratio), atten, float(np.float32(dw) / ratio))
+    info = _lib.CPhInfo()
+    assert lib.apt_ph_plan(l, m, taps.ctypes.data, taps.size, C.byref(info), None, 0, None, 0) == 0
+    if in_rate == 11025 and work_rate == 20800:
+        # slow profile at 11025 Hz: 40 891 taps -> 50 per output, table too large for shared memory: generic kernel
+        assert info.usable in (0, 1)
+        if not info.usable:
+            return
+    assert info.usable == 1 and info.l == l and info.m == m and info.jpad % 4 == 0 and info.pitch % 32 == 4
+    table = np.zeros(l * info.jpad, np.float32)
+    xs = np.zeros(l, np.uint16)
+    assert lib.apt_ph_plan(l, m, taps.ctypes.data, taps.size, C.byref(info), table.ctypes.data, table.size, xs.ctypes.data, xs.size) == 0
+    table = table.reshape(l, info.jpad)
+    rng = np.random.default_rng(7)
+    x = (rng.standard_normal(m * 40 + 123) * 1000).astype(np.float32)
+    ref = oracle.fast_resampling(x, l, m, taps)
+    xp = np.concatenate([x.astype(np.float64), np.zeros(m + 200)])
+    k = np.arange(ref.size)
+    q, r = k // l, k % l
+    idx = (q * m + xs[r].astype(np.int64))[:, None] + np.arange(info.jpad)[None, :]
+    got = np.sum(table[r].astype(np.float64) * xp[idx], axis=1)
+    assert np.max(np.abs(got - ref)) <= 1e-5 * np.max(np.abs(ref))
+
+
+def test_wav_reader_and_writer_roundtrip(tmp_path):
+    """wav.rs:11-56 restated without hound: 16-bit mono, stereo (channel 0 kept), 8-bit (offset 128), 32-bit float; the
+    16-bit writer of resample.rs:53-66.  No GPU involved."""
+    import struct
+    import wave
+    from noaa_apt_b200 import wav
+    rng = np.random.default_rng(5)
+    pcm = rng.integers(-32768, 32767, 5000, dtype=np.int16)
+    p = str(tmp_path / "mono16.wav")
+    with wave.open(p, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(11025); w.writeframes(pcm.tobytes())
+    assert wav.info(p) == {"sample_rate": 11025, "channels": 1, "bits_per_sample": 16, "is_float": False, "frames": 5000}
+    x, rate = wav.load_wav(p)
+    assert rate == 11025 and np.array_equal(x, pcm.astype(np.float32))          # `as f32`: raw values
+    raw, _ = wav.load_wav_pcm16(p)
+    assert np.array_equal(raw, pcm)
+    # stereo: interleaved, channel 0 kept
+    st = np.stack([pcm, -pcm], axis=1).reshape(-1)
+    p2 = str(tmp_path / "stereo16.wav")
+    with wave.open(p2, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(48000); w.writeframes(st.tobytes())
+    x2, rate2 = wav.load_wav(p2)
+    assert rate2 == 48000 and np.array_equal(x2, pcm.astype(np.float32))
+    # 8-bit unsigned
+    u8 = rng.integers(0, 255, 1000, dtype=np.uint8)
+    p3 = str(tmp_path / "mono8.wav")
+    with wave.open(p3, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(1); w.setframerate(8000); w.writeframes(u8.tobytes())
+    x3, _ = wav.load_wav(p3)
+    assert np.array_equal(x3, u8.astype(np.float32) - 128)
+    # 32-bit float (format tag 3), written by hand, with an odd-sized LIST chunk in front of the data
+    f32 = rng.standard_normal(777).astype(np.float32)
+    p4 = str(tmp_path / "f32.wav")
+    body = (b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 3, 1, 96000, 96000 * 4, 4, 32) + b"LIST" + struct.pack("<I", 3) + b"abc\0" +
+            b"data" + struct.pack("<I", f32.nbytes) + f32.tobytes())
+    open(p4, "wb").write(b"RIFF" + struct.pack("<I", len(body)) + body)
+    x4, rate4 = wav.load_wav(p4)
+    assert rate4 == 96000 and np.array_equal(x4, f32)
+    # writer
+    p5 = str(tmp_path / "out.wav")
+    wav.write_wav_i16(p5, pcm, 12480)
+    with wave.open(p5) as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 12480, 5000)
+        assert np.array_equal(np.frombuffer(w.readframes(5000), dtype="<i2"), pcm)
+    import noaa_apt_b200 as na
+    with pytest.raises(na.err.Io):
+        wav.load_wav(str(tmp_path / "missing.wav"))

@@ -99,3 +99,24 @@ def test_decode_image_u8_end_to_end(rows, contrast, percent):
     pcm = synth.apt_pcm16(11025, 150, seed=12)
     img16, _ = image.decode_image_u8(na.Context(), na.Settings(), pcm, 11025, True, contrast, percent)
     assert np.array_equal(img16, img)
+
+
+def test_quantize_i16_and_resample_tool(tmp_path):
+    """wav.rs:71-85 on the device, bit-exact; resample.rs:17-71 end to end on a WAV written by the stdlib."""
+    import wave
+    from noaa_apt_b200 import wav
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(50000) * 3000).astype(np.float32)
+    assert np.array_equal(wav.quantize_i16(x), oracle.quantize_i16(x))
+    assert np.array_equal(wav.quantize_i16(-np.abs(x) - 1), oracle.quantize_i16(-np.abs(x) - 1))   # negative maximum: saturation
+    pcm = synth.apt_pcm16(11025, 3, seed=1)
+    src, dst = str(tmp_path / "in.wav"), str(tmp_path / "out.wav")
+    with wave.open(src, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(11025); w.writeframes(pcm.tobytes())
+    for out_rate in (48000, 6000, 3675):                       # test/test.sh:47-49
+        n = wav.resample_wav(src, dst, out_rate, 40.0, 0.1)
+        ref = oracle.resample(pcm.astype(np.float32), 11025, out_rate, 40.0, 0.1)
+        got, rate = wav.load_wav_pcm16(dst)
+        assert rate == out_rate and n == ref.size == got.size
+        refq = oracle.quantize_i16(ref)
+        assert np.max(np.abs(got.astype(np.int32) - refq.astype(np.int32))) <= 1     # the resampled values agree to 1e-5
