@@ -321,8 +321,9 @@ int apt_ut_plan(uint32_t l, uint32_t m, const float *taps, size_t ntaps, apt_ut_
 
 /* Geometry and phase table of the phase-major resampler (noaa-apt_b200/csrc/kernels_ph.cuh), the kernel that serves
  * fast_resampling + demodulate for large interpolation factors (11025 / 22050 / 44100 Hz -> 12 480 Hz: L = 832 / 416 / 208).
- * Host logic only.  usable == 0: the shape does not fit.  Output k = l*q + r is
- *     sum_{j < jpad} table[r*jpad + j] * signal[m*q + xs[r] + j]        (samples beyond the end count as zero). */
+ * Host logic only.  usable == 0: the shape does not fit.  Four consecutive phases (group g = r / 4) share a window of
+ * jpad samples that starts at signal[m*q + xs[g] - 4]; output k = l*q + r is
+ *     sum_{i < jpad} table[(g*jpad + i)*4 + r%4] * signal[m*q + xs[g] - 4 + i]   (samples outside the signal count as zero). */
 typedef struct apt_ph_info {
     uint32_t usable, l, m, j, jpad, pitch, row_len, smem_bytes;
 } apt_ph_info;

@@ -1,5 +1,6 @@
 // C ABI (include/aptb200.h) over the decoder object and the stage kernels.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstddef>
@@ -26,6 +27,7 @@ int run_find_sync(apt_decoder *d, uint64_t nwork);
 int ensure_legacy_sync(apt_decoder *d);
 int redo_sync_legacy(apt_decoder *d);
 int materialise_stages(apt_decoder *d);
+extern std::atomic<int> g_jobs_in_flight[64];
 }  // namespace aptb200
 
 namespace {
@@ -641,6 +643,7 @@ int submit_common(apt_decoder *d, const void *signal, int format, uint64_t n, in
                                      d->job_d2h_floats * elem, cudaMemcpyDeviceToHost, d->stream));
     }
     d->in_flight = true;
+    if (d->device >= 0 && d->device < 64) g_jobs_in_flight[d->device].fetch_add(1, std::memory_order_relaxed);
     return APT_OK;
 }
 
@@ -662,6 +665,7 @@ extern "C" int apt_decoder_wait(apt_decoder *d, uint64_t *nout) {
     if (!d->in_flight) return d->job_status;
     APT_CUDA(cudaSetDevice(d->device));
     d->in_flight = false;
+    if (d->device >= 0 && d->device < 64) g_jobs_in_flight[d->device].fetch_sub(1, std::memory_order_relaxed);
     static const bool trace = getenv("APTB200_TRACE_HOST") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     APT_CUDA(cudaStreamSynchronize(d->stream));

@@ -2,6 +2,7 @@
 #include "decoder.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -367,10 +368,13 @@ static int enqueue_front(apt_decoder *d, const void *in, int format, uint64_t n,
 }
 
 // Enqueues the whole of decode() on the decoder's stream.  `in` and `rows_out` are device pointers.
+std::atomic<int> g_jobs_in_flight[64];      // per CUDA device: decodes submitted and not yet waited for
+
 int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int sync, float *rows_out,
                     const void *host_chunked) {
     const Plan &p = d->plan;
-    const LaunchCtx c{d->stream, d->sm_count};
+    LaunchCtx c{d->stream, d->sm_count};
+    c.busy = d->device >= 0 && d->device < 64 && g_jobs_in_flight[d->device].load(std::memory_order_relaxed) > 0 ? 1 : 0;
     const uint64_t nwork = plan_work_len(p, n);
     d->job_work = nwork;
     d->ev_used = 0;

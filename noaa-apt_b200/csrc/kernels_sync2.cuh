@@ -94,6 +94,9 @@ __device__ __forceinline__ u32 warp_excl_sum(u32 v, u32 lane, u32 &total) {
 __device__ __forceinline__ void cp_async16(float *dst, const float *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(Rec *dst, const Rec *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -452,7 +455,7 @@ k_resolve_roots(const TileDesc *__restrict__ desc, const Rec *__restrict__ pool,
                 lnp[k] = dl[k].np;
                 const Rec *src = pool + dl[k].off + dl[k].ns;
                 if (dl[k].np <= kResolveCache) {
-                    for (u32 i = lane; i < dl[k].np; i += 32) s_p[warp][k][i] = src[i];
+                    for (u32 i = lane; i < dl[k].np; i += 32) cp_async8(&s_p[warp][k][i], src + i);
                     lst[k] = s_p[warp][k];
                 } else {
                     lst[k] = src;
@@ -461,9 +464,12 @@ k_resolve_roots(const TileDesc *__restrict__ desc, const Rec *__restrict__ pool,
         }
         const Rec *cand = pool + d.off;
         if (d.ns <= kResolveCache) {
-            for (u32 i = lane; i < d.ns; i += 32) s_s[warp][i] = cand[i];
+            for (u32 i = lane; i < d.ns; i += 32) cp_async8(&s_s[warp][i], cand + i);
             cand = s_s[warp];
         }
+        // all three lists are in flight together (a load-then-store loop pays one L2 round trip per 32 records)
+        cp_async_commit_group();
+        cp_async_wait_all();
         __syncwarp();
         u32 cnt = 0;
         const u32 tile_begin = t * tile_w;                  // correlation indices fit 32 bits (N_w < 2^32)

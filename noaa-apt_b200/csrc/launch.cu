@@ -193,11 +193,11 @@ int launch_polyphase_ph(const LaunchCtx &c, const void *signal, int format, u64 
     const float *sf = static_cast<const float *>(signal);
     const int16_t *si = static_cast<const int16_t *>(signal);
     const bool pcm = format == APT_PCM16;
-    switch (pp.jpad) {
-    case 20: if (pcm) launch(k_polyphase_ph<int16_t, 20>, si); else launch(k_polyphase_ph<float, 20>, sf); break;
-    case 36: if (pcm) launch(k_polyphase_ph<int16_t, 36>, si); else launch(k_polyphase_ph<float, 36>, sf); break;
-    case 68: if (pcm) launch(k_polyphase_ph<int16_t, 68>, si); else launch(k_polyphase_ph<float, 68>, sf); break;
-    default: return fail(APT_ERR_BAD_ARG, "phase-major resampler: no instantiation for %u taps per output", pp.jpad);
+    switch (pp.jpad) {      // the shared window of a group of four phases
+    case 24: if (pcm) launch(k_polyphase_ph<int16_t, 24>, si); else launch(k_polyphase_ph<float, 24>, sf); break;
+    case 44: if (pcm) launch(k_polyphase_ph<int16_t, 44>, si); else launch(k_polyphase_ph<float, 44>, sf); break;
+    case 84: if (pcm) launch(k_polyphase_ph<int16_t, 84>, si); else launch(k_polyphase_ph<float, 84>, sf); break;
+    default: return fail(APT_ERR_BAD_ARG, "phase-major resampler: no instantiation for a window of %u samples", pp.jpad);
     }
     APT_CUDA(cudaGetLastError());
     return APT_OK;
@@ -283,9 +283,33 @@ int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32
 int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const RootIndex &ri_in, u32 *positions,
                 u32 max_positions, SyncResult *result, const PickScratch *scratch) {
     RootIndex ri = ri_in;
-    static const bool force_grid = getenv("APTB200_GRID_PICK") != nullptr;
+    // Which parallel orbit walk: APTB200_PICK = compress | cluster | grid forces one; by default the whole-GPU cooperative
+    // walk (39 us, but it needs every SM) when the device is otherwise idle, the 8-CTA cluster walk (60 us on 8 SMs) when
+    // other recordings are in flight on other streams (batch: 338 k vs 280 k Msamples/s at 64 streams).
+    static const int forced = [] {
+        const char *e = getenv("APTB200_PICK");
+        if (getenv("APTB200_GRID_PICK")) return 2;
+        if (!e) return -1;
+        return !strcmp(e, "compress") ? 0 : !strcmp(e, "cluster") ? 1 : !strcmp(e, "grid") ? 2 : -1;
+    }();
+    const int mode = forced >= 0 ? forced : (c.busy ? 1 : 2);
     const u64 nr = (ncorr + row - 1) / row;
-    if (scratch && !force_grid && nr <= 20000) {
+    if (scratch && mode == 0 && nr + 1 <= static_cast<u64>(kPickEMax - 2) * kPickR) {
+        // compressed walk: J0 and E = J0^8 over the whole GPU, then one CTA (see kernels_sync.cuh)
+        const size_t smem = (3ull * kPickKMax + kPickEMax) * sizeof(u32);
+        static const bool attr_ok =
+            cudaFuncSetAttribute(k_pick_final, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) == cudaSuccess;
+        if (attr_ok) {
+            PickScratch sc = *scratch;
+            const unsigned grid = (sc.cap + 1 + 255) / 256;       // one thread per possible node; the kernels know how many exist
+            k_pick_j0<<<grid, 256, 0, c.stream>>>(ncorr, row, dist, ri, positions, max_positions, result, sc);
+            k_pick_e8<<<grid, 256, 0, c.stream>>>(ncorr, row, ri, max_positions, result, sc);
+            k_pick_final<<<1, 1024, smem, c.stream>>>(ncorr, nwork, row, dist, ri, positions, max_positions, result, sc);
+            APT_CUDA(cudaGetLastError());
+            return APT_OK;
+        }
+    }
+    if (scratch && mode <= 1 && nr <= 20000) {
         // one 8-CTA cluster, jump tables in distributed shared memory (larger recordings: the whole-GPU cooperative grid)
         const size_t smem = 2ull * kPickClusterPer * sizeof(u32);
         static const int attr_ok = [&] {
@@ -442,7 +466,7 @@ int launch_quantize_i16(const LaunchCtx &c, const float *x, u64 n, PostCtl *ctl,
 static size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
 size_t pick_scratch_bytes(u32 max_blocks, u32 max_positions, u32 cap) {
-    return align_up((static_cast<size_t>(max_blocks) + 1) * 4) + 4 * align_up((static_cast<size_t>(cap) + 1) * 4) +
+    return align_up((static_cast<size_t>(max_blocks) + 1) * 4) + 5 * align_up((static_cast<size_t>(cap) + 1) * 4) +
            align_up((static_cast<size_t>(max_positions) + 1) * 4) + align_up(8);
 }
 
@@ -459,6 +483,7 @@ PickScratch pick_scratch_carve(void *base, u32 max_blocks, u32 max_positions, u3
     s.cand_peak = take(static_cast<size_t>(cap) + 1);
     s.ja = take(static_cast<size_t>(cap) + 1);
     s.jb = take(static_cast<size_t>(cap) + 1);
+    s.idx = take(static_cast<size_t>(cap) + 1);
     s.orbit = take(static_cast<size_t>(max_positions) + 1);
     s.ticket = take(2);
     s.cap = cap;

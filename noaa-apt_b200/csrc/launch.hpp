@@ -72,7 +72,8 @@ struct PickScratch {
     u32 *block_off;    // [nblocks + 1] exclusive scan of root_count (dense root numbering)
     u32 *cand_s;       // [cap + 1] start position of each candidate
     u32 *cand_peak;    // [cap + 1] firstroot(start)
-    u32 *ja, *jb;      // [cap + 1] jump tables (J0, and the global ping-pong pair when smem is too small)
+    u32 *ja, *jb;      // [cap + 1] jump tables (J0, and the global ping-pong pair when smem is too small / E = J0^8)
+    u32 *idx;          // [cap + 1] compressed walk: image flag, then compact id of a node
     u32 *orbit;        // [max_positions + 1]
     u32 *ticket;       // [2] last-CTA tickets of k_roots / k_pick_links (zero between launches)
     u32 cap;           // candidate capacity
@@ -136,7 +137,7 @@ struct UtPlan {
 constexpr u32 kPhTilePeriods = 32;   // periods (= l outputs each) per tile of the phase-major resampler
 struct PhPlan {
     u32 l, m;
-    u32 j, jpad;       // taps per output, padded to the kernel's instantiation (20 / 36 / 68)
+    u32 j, jpad;       // taps per output; jpad = WIN, the window four consecutive phases share (24 / 44 / 84 samples)
     u32 pitch;         // floats per shared-memory input row
     u32 row_len;       // samples staged per row
     u32 smem_bytes;
@@ -145,6 +146,8 @@ struct PhPlan {
 struct LaunchCtx {
     cudaStream_t stream;
     int sm_count;
+    int busy = 0;      // other jobs are in flight on this device: prefer kernels with a small footprint (the 8-CTA cluster
+                       // picker leaves 140 SMs to the other streams; alone, the whole-GPU cooperative walk is faster)
 };
 
 // fast_resampling (dsp.rs:186-289), optionally fused with demodulate (dsp.rs:350-383).
@@ -210,7 +213,8 @@ int launch_polyphase_tiled(const LaunchCtx &c, const float *signal, u64 len, con
                            bool envelope, float cosphi2, float sinphi, float *out);
 
 // Phase-major resampler (+ envelope) for large L (11025 / 22050 / 44100 Hz input).  make_ph_plan returns false when the
-// shape does not fit (then the generic kernel serves it); table = [l][jpad] taps, xs = [l] window starts, both go to HBM.
+// shape does not fit (then the generic kernel serves it); table = [l/4][jpad][4] taps laid out against the groups' windows,
+// xs = [l/4] window starts (row index), both go to HBM.
 bool make_ph_plan(u32 l, u32 m, const std::vector<float> &taps, PhPlan &pp, std::vector<float> &table,
                   std::vector<unsigned short> &xs);
 // Tiles of 32 periods (32*l outputs) [tile_begin, tile_end) (tile_end == 0: all); `signal` is the address sample 0 would have.

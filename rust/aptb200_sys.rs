@@ -61,4 +61,40 @@ extern "C" {
                       out: *mut c_float, cap: u64, nout: *mut u64, cb: apt_status_cb, user: *mut c_void) -> c_int;
     pub fn apt_decode_pcm16(pcm: *const i16, n: u64, input_rate: u32, s: *const apt_settings, sync: c_int,
                             out: *mut c_float, cap: u64, nout: *mut u64, cb: apt_status_cb, user: *mut c_void) -> c_int;
+    pub fn apt_cache_clear();
+
+    // WAV files and the resample tool (wav.rs, resample.rs)
+    pub fn apt_wav_info_read(path: *const c_char, info: *mut apt_wav_info) -> c_int;
+    pub fn apt_wav_load(path: *const c_char, out: *mut c_float, cap: u64, n: *mut u64, sample_rate: *mut u32) -> c_int;
+    pub fn apt_wav_load_pcm16(path: *const c_char, out: *mut i16, cap: u64, n: *mut u64, sample_rate: *mut u32) -> c_int;
+    pub fn apt_wav_write_i16(path: *const c_char, samples: *const i16, n: u64, sample_rate: u32) -> c_int;
+    pub fn apt_quantize_i16(signal: *const c_float, n: u64, out: *mut i16) -> c_int;
+    pub fn apt_resample_wav(input_path: *const c_char, output_path: *const c_char, output_rate: u32, atten: c_float,
+                            delta_w_pi: c_float, nout: *mut u64) -> c_int;
+
+    // image stage (front of noaa_apt::process)
+    pub fn apt_decode_image_u8(signal: *const c_void, format: c_int, n: u64, input_rate: u32, s: *const apt_settings,
+                               sync: c_int, contrast: c_int, percent: c_float, out: *mut u8, cap: u64, nout: *mut u64,
+                               info: *mut apt_image_info, cb: apt_status_cb, user: *mut c_void) -> c_int;
+    pub fn apt_map_signal_u8(signal: *const c_float, n: u64, low: c_float, high: c_float, out: *mut u8) -> c_int;
+    pub fn apt_contrast_bounds(signal: *const c_float, n: u64, contrast: c_int, percent: c_float,
+                               info: *mut apt_image_info) -> c_int;
+    pub fn apt_telemetry_rows(signal: *const c_float, n: u64, mean_a: *mut c_float, mean_b: *mut c_float,
+                              variance: *mut c_float) -> c_int;
 }
+
+pub const APT_F32: c_int = 0;
+pub const APT_PCM16: c_int = 1;
+pub const APT_CONTRAST_MINMAX: c_int = 0;
+pub const APT_CONTRAST_PERCENT: c_int = 1;
+pub const APT_CONTRAST_TELEMETRY: c_int = 2;
+pub const APT_ERR_IO: c_int = 11;
+
+#[repr(C)]
+#[derive(Default, Clone, Copy)]
+pub struct apt_wav_info { pub sample_rate: u32, pub channels: u32, pub bits_per_sample: u32, pub is_float: u32, pub frames: u64 }
+
+#[repr(C)]
+#[derive(Default, Clone, Copy)]
+pub struct apt_image_info { pub low: f32, pub high: f32, pub rows: u64, pub telemetry_row: u64,
+                            pub wedges_a: [f32; 16], pub wedges_b: [f32; 16] }

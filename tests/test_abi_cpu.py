@@ -307,8 +307,8 @@ def test_uniform_tap_plan_rejects_other_ratios(na):
 @pytest.mark.parametrize("in_rate,work_rate,atten,dfreq", [(11025, 12480, 30.0, 1000.0), (22050, 12480, 30.0, 1000.0),
                                                            (44100, 12480, 30.0, 1000.0), (11025, 20800, 40.0, 500.0)])
 def test_phase_major_plan_reproduces_fast_resampling(in_rate, work_rate, atten, dfreq):
-    """Host logic of kernels_ph.cuh: y[l*q + r] = sum_j table[r][j] * x[m*q + xs[r] + j] must be fast_resampling
-    (dsp.rs:186-289) -- emulated in numpy (float64 accumulation) against the oracle."""
+    """Host logic of kernels_ph.cuh: y[l*q + r] = sum_i table[r/4][i][r%4] * x[m*q + xs[r/4] - 4 + i] must be
+    fast_resampling (dsp.rs:186-289) -- emulated in numpy (float64 accumulation) against the oracle."""
     import math
     import oracle
     from noaa_apt_b200 import _lib
@@ -325,19 +325,20 @@ def test_phase_major_plan_reproduces_fast_resampling(in_rate, work_rate, atten, 
         assert info.usable in (0, 1)
         if not info.usable:
             return
-    assert info.usable == 1 and info.l == l and info.m == m and info.jpad % 4 == 0 and info.pitch % 32 == 4
+    assert info.usable == 1 and info.l == l and info.m == m and info.jpad in (24, 44, 84) and info.pitch % 32 == 4
     table = np.zeros(l * info.jpad, np.float32)
-    xs = np.zeros(l, np.uint16)
+    xs = np.zeros(l // 4, np.uint16)
     assert lib.apt_ph_plan(l, m, taps.ctypes.data, taps.size, C.byref(info), table.ctypes.data, table.size, xs.ctypes.data, xs.size) == 0
-    table = table.reshape(l, info.jpad)
+    assert (xs % 4 == 0).all()                              # 16-byte aligned windows
+    table = table.reshape(l // 4, info.jpad, 4)
     rng = np.random.default_rng(7)
     x = (rng.standard_normal(m * 40 + 123) * 1000).astype(np.float32)
     ref = oracle.fast_resampling(x, l, m, taps)
-    xp = np.concatenate([x.astype(np.float64), np.zeros(m + 200)])
+    xp = np.concatenate([np.zeros(4), x.astype(np.float64), np.zeros(m + 200)])   # xp[4 + i] = x[i]
     k = np.arange(ref.size)
     q, r = k // l, k % l
-    idx = (q * m + xs[r].astype(np.int64))[:, None] + np.arange(info.jpad)[None, :]
-    got = np.sum(table[r].astype(np.float64) * xp[idx], axis=1)
+    idx = (q * m + xs[r // 4].astype(np.int64))[:, None] + np.arange(info.jpad)[None, :]   # row index: signal index + 4
+    got = np.sum(table[r // 4, :, r % 4].astype(np.float64) * xp[idx], axis=1)
     assert np.max(np.abs(got - ref)) <= 1e-5 * np.max(np.abs(ref))
 
 
