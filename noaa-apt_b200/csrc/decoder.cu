@@ -410,8 +410,10 @@ int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int 
                 Prof pr(d, "sync_pick");
                 const RootIndex ri{d->d_roots2, d->d_root_count, d->d_tile_base, d->d_desc, d->d_by_id, &d->d_ctl->root_cursor,
                                    d->tile_w, ntiles};
+                int nk = 1;
                 APT_TRY(launch_pick(c, ncorr, nwork, p.row, p.dist, ri, d->d_pos, d->max_positions, d->d_res,
-                                    d->use_parallel_pick && d->d_pick ? &d->pick : nullptr));
+                                    d->use_parallel_pick && d->d_pick ? &d->pick : nullptr, &nk));
+                d->launches += static_cast<uint64_t>(nk - 1);               // Prof counted one
             }
             if (d->cb) d->cb(0.9f, "Resampling to 4160", d->cb_user);       // decode.rs:154
             Prof pr(d, "gather_rows");

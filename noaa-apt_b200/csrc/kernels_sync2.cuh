@@ -396,7 +396,7 @@ k_lowpass_records(const float *__restrict__ e, u64 n, u64 ncorr, const __grid_co
 // from an atomic cursor (ids are labels: any disjoint ranges do) -> tile_base[t], root position by id -> by_id.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kResolveThreads = 128;
-constexpr int kResolveCache = 256;               // records of one list kept in shared memory (longer lists: global)
+constexpr int kResolveCache = 192;               // records of one list kept in shared memory (longer lists: global); 21 KB per CTA: 10 CTAs per SM
 
 // first record of the ascending list L[0..np) whose value exceeds v; np if none
 __device__ __forceinline__ u32 first_exceeding(const Rec *L, u32 np, float v) {

@@ -184,7 +184,13 @@ __device__ __forceinline__ void ut_role(const UtParams<MAXV> &prm, const UtGeom 
     // both warps are past the FMA loop (nobody reads the samples any more) and have published
     __syncwarp();
     if (lane == 0) mbar_arrive(xch_bar);
+#if defined(APTB200_UT_XCH_SLEEP) && APTB200_UT_XCH_SLEEP > 0
+    // the lighter role (3 of the 7 pairs) waits here for ~a quarter of a block's time: back off between polls so that its
+    // try_wait loop (55 iterations x 4 instructions per block in the first capture) does not eat issue slots
+    while (!mbar_try_wait(xch_bar, parity)) __nanosleep(APTB200_UT_XCH_SLEEP);
+#else
     mbar_wait(xch_bar, parity);
+#endif
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
         float r[2 * NPR];

@@ -281,8 +281,11 @@ int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32
 }
 
 int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const RootIndex &ri_in, u32 *positions,
-                u32 max_positions, SyncResult *result, const PickScratch *scratch) {
+                u32 max_positions, SyncResult *result, const PickScratch *scratch, int *kernels_launched) {
     RootIndex ri = ri_in;
+    int dummy = 0;
+    int &nk = kernels_launched ? *kernels_launched : dummy;
+    nk = 1;
     // Which parallel orbit walk: APTB200_PICK = compress | cluster | grid forces one; by default the whole-GPU cooperative
     // walk (39 us, but it needs every SM) when the device is otherwise idle, the 8-CTA cluster walk (60 us on 8 SMs) when
     // other recordings are in flight on other streams (batch: 338 k vs 280 k Msamples/s at 64 streams).
@@ -306,6 +309,7 @@ int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, con
             k_pick_e8<<<grid, 256, 0, c.stream>>>(ncorr, row, ri, max_positions, result, sc);
             k_pick_final<<<1, 1024, smem, c.stream>>>(ncorr, nwork, row, dist, ri, positions, max_positions, result, sc);
             APT_CUDA(cudaGetLastError());
+            nk = 3;
             return APT_OK;
         }
     }
@@ -333,6 +337,7 @@ int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, con
             k_pick_j0<<<j0_grid, 256, 0, c.stream>>>(ncorr, row, dist, ri, positions, max_positions, result, sc);
             APT_CUDA(cudaGetLastError());
             APT_CUDA(cudaLaunchKernelEx(&cfg, k_pick_cluster, ncorr, nwork, row, dist, ri, positions, max_positions, result, sc));
+            nk = 2;
             return APT_OK;
         }
     }

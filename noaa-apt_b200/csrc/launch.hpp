@@ -174,7 +174,8 @@ int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32
                  SyncResult *result, const PickScratch *scratch /* nullptr: no dense numbering */);
 // orbit walk -> sync positions (decode.rs:241-253).
 int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const RootIndex &ri, u32 *positions,
-                u32 max_positions, SyncResult *result, const PickScratch *scratch /* nullptr: sequential walk */);
+                u32 max_positions, SyncResult *result, const PickScratch *scratch /* nullptr: sequential walk */,
+                int *kernels_launched = nullptr);
 // Fused sync stage (kernels_sync2.cuh): low-pass + correlation + per-tile records, then the roots; f and corr never reach HBM.
 u32 records_tile(u32 pixel_width);   // correlation positions per tile
 int launch_lowpass_records(const LaunchCtx &c, const float *e, u64 n, u64 ncorr, const float *taps_host, u32 ntaps,
