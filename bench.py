@@ -480,26 +480,51 @@ def run_b200(args, rank, local_rank, world):
             rates = other_rates(na, lib, cset, local_rank, timed, K)
 
     # ---- parity of what was timed: rows and sync positions against the CPU oracle (outside the timed regions) ----
+    # Sync positions must be the oracle's.  The one tolerated exception is a TIE: the picker compares correlation values
+    # with a strict `>` (decode.rs:250) and the device's correlation differs from the reference's sequential f32 sum by
+    # ~1e-7 relative, so where two neighbouring candidates are closer than that the choice -- in the reference as on the
+    # device -- is decided by the last bit (seed 15: 64847.316 vs 64847.312 one sample apart).  Such a position may differ
+    # by at most one work sample and is reported; its image row is excluded from the value comparison.
     import oracle
     check = n <= 200_000_000                 # the 10-hour recording of c3 would keep the oracle busy for minutes
     refs = []
     if check:
         with ThreadPoolExecutor(max_workers=n_seeds) as ex:
             refs = list(ex.map(lambda x: oracle.decode_steps(x, rate), x_f32))
-    worst = 0.0
+    worst, ties, tie_margin = 0.0, 0, 0.0
     for k in range(len(refs)):
         ref, st = refs[k]
-        if not np.array_equal(sync_dev[k], st["sync_pos"]):
-            raise SystemExit(f"bench: sync positions of recording {k} differ from the oracle")
+        pos_ref = st["sync_pos"].astype(np.int64)
+        pos_gpu = sync_dev[k].astype(np.int64)
+        if pos_gpu.size != pos_ref.size:
+            raise SystemExit(f"bench: recording {k}: {pos_gpu.size} sync positions, oracle {pos_ref.size}")
+        bad = np.nonzero(pos_gpu != pos_ref)[0]
+        tie_rows = set()
+        if bad.size:
+            _, corr = oracle.find_sync(st["filtered"], settings.work_rate, want_corr=True)
+            for j in bad:
+                a, b = int(pos_ref[j]), int(pos_gpu[j])
+                margin = abs(float(corr[a]) - float(corr[b])) / max(abs(float(corr[a])), 1e-30) if max(a, b) < corr.size else 1.0
+                if abs(a - b) > 1 or margin > 1e-6:
+                    raise SystemExit(f"bench: sync position {j} of recording {k} differs from the oracle: {b} vs {a} "
+                                     f"(correlation margin {margin:.2e}): not a tie")
+                ties += 1
+                tie_margin = max(tie_margin, margin)
+                tie_rows.add(int(j))
+        keep = np.ones(ref.size // 2080, dtype=bool)
+        for j in tie_rows:
+            if j < keep.size:
+                keep[j] = False
         for name, rows in (("device", rows_dev[k]), ("e2e", rows_e2e[k]), ("e2e_pcm16", rows_p16[k])):
             if rows.size != ref.size:
                 raise SystemExit(f"bench: {name} rows of recording {k}: {rows.size} values, oracle {ref.size}")
-            err = nerr(rows, ref)
+            err = nerr(rows.reshape(-1, 2080)[keep], ref.reshape(-1, 2080)[keep])
             worst = max(worst, err)
             if err > TOL:
                 raise SystemExit(f"bench: {name} rows of recording {k} differ from the oracle: {err:.3e} > {TOL}")
     parity = {"checked": f"{n_seeds} distinct recordings x (device-resident, e2e f32, e2e PCM16) rows + sync positions vs the "
-                         f"CPU oracle on the full recording", "sync_positions_equal": True, "max_normalised_error": worst,
+                         f"CPU oracle on the full recording", "sync_positions_equal": ties == 0, "sync_position_ties": ties,
+              "tie_correlation_margin": tie_margin, "max_normalised_error": worst,
               "tolerance": TOL} if check else {"checked": "skipped: recording too long for the oracle inside the bench "
                                                           "(tests/test_gpu_fullsize.py covers the chunked path)"}
 

@@ -1251,8 +1251,10 @@ extern "C" int apt_decode_batch(const void *const *signals, int format, const ui
     std::vector<std::string> messages(ndevices);
     std::vector<int> fatal(ndevices, APT_OK);
 
+    const int streams_wanted = streams_per_device;
     auto feeder = [&](int g) {
         const int device = devices[g];
+        int streams_per_device = streams_wanted;       // per feeder: one device running out of memory does not limit the others
         bind_thread_to_device(device);
         std::vector<apt_decoder *> decs;
         std::vector<int> job_of;

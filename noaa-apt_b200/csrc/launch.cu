@@ -2,6 +2,7 @@
 #include "launch.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -280,6 +281,22 @@ int launch_roots(const LaunchCtx &c, const float *corr, u64 ncorr, u32 dist, u32
     return fail(APT_ERR_BAD_ARG, "work rate too high for the sync picker (min_distance %u)", dist);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device; cache the outcome per device (0 unknown, 1 ok, -1 refused).
+constexpr int kMaxDevices = 64;
+template <typename K>
+static bool smem_attr_once(std::atomic<signed char> *flags, K kern, size_t smem) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices)
+        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) == cudaSuccess;
+    signed char v = flags[dev].load(std::memory_order_acquire);
+    if (v == 0) {
+        v = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) == cudaSuccess ? 1 : -1;
+        if (v < 0) cudaGetLastError();
+        flags[dev].store(v, std::memory_order_release);
+    }
+    return v > 0;
+}
+
 int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, const RootIndex &ri_in, u32 *positions,
                 u32 max_positions, SyncResult *result, const PickScratch *scratch, int *kernels_launched) {
     RootIndex ri = ri_in;
@@ -300,9 +317,9 @@ int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, con
     if (scratch && mode == 0 && nr + 1 <= static_cast<u64>(kPickEMax - 2) * kPickR) {
         // compressed walk: J0 and E = J0^8 over the whole GPU, then one CTA (see kernels_sync.cuh)
         const size_t smem = (3ull * kPickKMax + kPickEMax) * sizeof(u32);
-        static const bool attr_ok =
-            cudaFuncSetAttribute(k_pick_final, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) == cudaSuccess;
-        if (attr_ok) {
+        // the attribute belongs to the (function, device) pair: one flag per device, not one per process
+        static std::atomic<signed char> attr_final[kMaxDevices];
+        if (smem_attr_once(attr_final, k_pick_final, smem)) {
             PickScratch sc = *scratch;
             const unsigned grid = (sc.cap + 1 + 255) / 256;       // one thread per possible node; the kernels know how many exist
             k_pick_j0<<<grid, 256, 0, c.stream>>>(ncorr, row, dist, ri, positions, max_positions, result, sc);
@@ -316,10 +333,8 @@ int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, con
     if (scratch && mode <= 1 && nr <= 20000) {
         // one 8-CTA cluster, jump tables in distributed shared memory (larger recordings: the whole-GPU cooperative grid)
         const size_t smem = 2ull * kPickClusterPer * sizeof(u32);
-        static const int attr_ok = [&] {
-            return cudaFuncSetAttribute(k_pick_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) == cudaSuccess;
-        }();
-        if (attr_ok) {
+        static std::atomic<signed char> attr_cluster[kMaxDevices];
+        if (smem_attr_once(attr_cluster, k_pick_cluster, smem)) {
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(8);
             cfg.blockDim = dim3(1024);
@@ -386,9 +401,10 @@ int launch_lowpass_records(const LaunchCtx &c, const float *e, u64 n, u64 ncorr,
     const int tb = records_tb();
     const size_t smem = 2ull * kRecWarps * rec_smem_floats(tb) * sizeof(float);
     auto launch = [&](auto kern) {
+        if (smem > (48u << 10))      // per device, so not cached in the static below (only an experimental tile height gets here)
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         static const int per_sm = [&] {
             int v = 0;
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, 32 * kRecWarps, smem) != cudaSuccess || v < 1) v = 1;
             return v;
         }();
