@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arms (0: all available, at most one per recording)")
     ap.add_argument("--cpu-seconds", type=float, default=0.0, help="cap the recording length the CPU arms decode (0: full length)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed-base", type=int, default=0,
+                    help="first recording seed of rank 0 (rank r uses seed-base + 4r ...); 12 puts the tied recording, seed 15, on one GPU")
     ap.add_argument("--no-extras", action="store_true", help="skip the single-recording and other-rate measurements")
     return ap.parse_args()
 
@@ -293,7 +295,7 @@ def run_b200(args, rank, local_rank, world):
     # B recordings per GPU, one decoder (= one CUDA stream + workspaces) each; up to 4 distinct seeds are generated and
     # replicated into separate device buffers
     n_seeds = min(B, 4)
-    pcms = make_recordings(rate, args.seconds, [rank * 4 + k for k in range(n_seeds)])
+    pcms = make_recordings(rate, args.seconds, [args.seed_base + rank * 4 + k for k in range(n_seeds)])
     if repeat > 1:
         # 900 s = 1800 whole lines and 2 160 000 carrier cycles: the repetition is a continuous APT signal
         pcms = [np.tile(p, repeat) for p in pcms]
@@ -527,6 +529,15 @@ def run_b200(args, rank, local_rank, world):
               "tie_correlation_margin": tie_margin, "max_normalised_error": worst,
               "tolerance": TOL} if check else {"checked": "skipped: recording too long for the oracle inside the bench "
                                                           "(tests/test_gpu_fullsize.py covers the chunked path)"}
+
+    if world > 1 and check:                  # every rank checked its own recordings (and aborts on a mismatch): sum the ties
+        t = torch.tensor([float(ties), float(len(refs))], device=dev)
+        dist.all_reduce(t)
+        w = torch.tensor([worst, tie_margin], device=dev)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        parity.update({"checked": parity["checked"].replace(f"{n_seeds} distinct", f"{int(t[1].item())} distinct (all ranks)"),
+                       "sync_position_ties": int(t[0].item()), "sync_positions_equal": int(t[0].item()) == 0,
+                       "max_normalised_error": float(w[0].item()), "tie_correlation_margin": float(w[1].item())})
 
     line = None
     if rank == 0:

@@ -101,9 +101,24 @@ int alloc_sync_buffers(apt_decoder *d) {
     if (d->use_records) {
         d->tile_w = records_tile(p.dec);
         d->max_tiles = static_cast<uint32_t>((d->max_corr + d->tile_w - 1) / d->tile_w);
-        uint64_t cap = std::max<uint64_t>(d->max_corr / 2, 1u << 16);
-        if (const char *e = getenv("APTB200_RECORD_POOL")) cap = std::max<uint64_t>(strtoull(e, nullptr, 10), 64);
-        d->pool_cap = static_cast<uint32_t>(std::min<uint64_t>(cap, 1u << 30));
+        // Record pool: every tile owns a region of kRegion records (a noisy recording has ~200 per tile of 1920 positions: a
+        // third), tiles with more take theirs from a shared overflow area behind the regions (one atomic, rare).  A
+        // recording that does not fit even that (silence, ramps: every position a record) is decoded by the exact-order legacy
+        // kernels (kSyncRedo).  APTB200_RECORD_POOL=<records> shrinks the pool (tests of that path): no regions then.
+        constexpr uint64_t kRegion = 640;
+        uint64_t region = kRegion;
+        if (const char *e = getenv("APTB200_RECORD_REGION")) region = strtoull(e, nullptr, 10);
+        uint64_t cap = static_cast<uint64_t>(d->max_tiles) * region + std::max<uint64_t>(d->max_corr / 8, 1u << 16);
+        if (const char *e = getenv("APTB200_RECORD_POOL")) {
+            cap = std::max<uint64_t>(strtoull(e, nullptr, 10), 64);
+            if (static_cast<uint64_t>(d->max_tiles) * region > cap / 2) region = 0;
+        }
+        if (cap > (1u << 30)) {                  // hours at once: cap the pool, give the regions what is left of it
+            cap = 1u << 30;
+            region = std::min<uint64_t>(region, cap / 2 / std::max<uint32_t>(d->max_tiles, 1));
+        }
+        d->pool_cap = static_cast<uint32_t>(cap);
+        d->pool_region = static_cast<uint32_t>(region);
         APT_CUDA(cudaMalloc(&d->d_ctl, sizeof(SyncCtl)));
         APT_CUDA(cudaMemset(d->d_ctl, 0, sizeof(SyncCtl)));
         APT_CUDA(cudaMalloc(&d->d_desc, static_cast<size_t>(d->max_tiles) * sizeof(TileDesc)));

@@ -398,7 +398,7 @@ int decoder_enqueue(apt_decoder *d, const void *in, int format, uint64_t n, int 
             {
                 Prof pr(d, "lowpass_records");
                 APT_TRY(launch_lowpass_records(c, d->d_e, nwork, ncorr, p.lp.data(), ntaps, p.dec, d->d_ctl, d->d_desc, d->d_pool,
-                                               d->pool_cap, ntiles));
+                                               d->pool_cap, d->pool_region, ntiles));
             }
             if (d->cb) d->cb(0.5f, "Syncing", d->cb_user);
             {

@@ -87,7 +87,7 @@ struct apt_decoder {
     float *d_e = nullptr;          // envelope           ("demodulation_result")
     // fused sync stage (kernels_sync2.cuh): f and corr never reach HBM; per-tile records -> roots
     bool use_records = false;      // the fused stage serves this plan (standard / fast / slow profiles)
-    aptb200::u32 tile_w = 0, max_tiles = 0, pool_cap = 0;
+    aptb200::u32 tile_w = 0, max_tiles = 0, pool_cap = 0, pool_region = 0;   // pool_region: records of a tile's own pool region
     aptb200::SyncCtl *d_ctl = nullptr;
     aptb200::TileDesc *d_desc = nullptr;
     aptb200::Rec *d_pool = nullptr;

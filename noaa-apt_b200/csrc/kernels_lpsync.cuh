@@ -33,6 +33,8 @@ namespace aptb200 {
 struct LpTaps {          // kernel parameter: warp-uniform operands
     float2 a_even[32];   // (c[2i], c[2i-1]), c[-1] = 0      -- used by the warps that own the even positions
     float2 a_odd[32];    // (c[2i+1], c[2i]), c[NT] = 0      -- ... the odd positions
+    float2 p[64];        // p[j+1] = (c[j], c[j+1]), j = -1 .. NT-1 -- one sample x the taps of two neighbouring outputs
+    float2 pd[72];       // pd[j+DEC] = (c[j], c[j+DEC]), j = -DEC .. NT-1 -- ... of two neighbouring PIXELS (DEC samples apart)
 };
 
 constexpr int kLpTile = 1856;   // (T + 38*PW - 1) / 16 <= 128 for PW <= 5: every phase is one pass of the CTA

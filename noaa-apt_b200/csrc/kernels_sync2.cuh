@@ -31,12 +31,15 @@ namespace aptb200 {
 
 // TB = rows of 32 low-passed samples per tile: 64 (two rounds of a warp per phase, 6.7 % halo, 19.3 KB of shared memory per
 // warp -> 11 warps per SM) or 32 (one round, 14 % halo, 10 KB -> 20 warps per SM).
-constexpr int kRecWarps = 1;                     // warps per CTA; every warp works on its own tiles, no CTA barrier
 constexpr int kRecRowPitch = 36;                 // floats per shared-memory row of 32 (+4: 16-byte accesses of 8
                                                  // consecutive rows hit 8 distinct bank groups)
 constexpr int kRecShift = 3;                     // box-sum row r lives in physical row r + 3 (aliases dead e rows)
 __host__ __device__ constexpr int rec_smem_floats(int tb) { return (tb + kRecShift) * kRecRowPitch; }
-__host__ __device__ constexpr int rec_ctas_per_sm(int tb, int nt) { return tb >= 64 ? 11 : (nt > 43 ? 12 : 20); }
+// NBUF = 2: the next tile's samples are in flight while the current tile is worked on; NBUF = 1: half the shared memory,
+// so nearly twice the warps per SM (the register file becomes the limit), each waiting for its own tile's samples.
+__host__ __device__ constexpr int rec_ctas_per_sm(int tb, int nt, int nbuf = 2) {
+    return nbuf == 2 ? (tb >= 64 ? 11 : (nt > 43 ? 12 : 20)) : (nt > 43 ? 12 : nt > 37 ? 16 : 20);
+}
 
 __host__ __device__ constexpr int rec_tile_outputs(int pw, int tb) {   // W: correlation outputs per tile (multiple of 32)
     return (32 * tb - 18 * 2 * pw - (2 * pw - 1)) / 32 * 32;
@@ -100,10 +103,14 @@ __device__ __forceinline__ void cp_async8(Rec *dst, const Rec *src) {
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int NT, int PW, int TB>
-__global__ void __launch_bounds__(32 * kRecWarps, rec_ctas_per_sm(TB, NT))
+// NW = 1 (what is instantiated): every warp is its own CTA.  NW > 1: the NW warps of a CTA take NW consecutive tiles and
+// meet at a CTA barrier before every phase, so that they share the fetched instruction lines (the kernel is ~3900
+// straight-line instructions per tile, 46 KB of code).  Measured at NW = 4 / 8 / 10 / 16 / 20: 49.5 / 49.5 / 55.6 / 65.9 /
+// 59.7 us against 47.6 us for NW = 1 -- instruction supply is not what bounds the kernel; kept as a template parameter only.
+template <int NT, int PW, int TB, int NBUF = 2, int NW = 1>
+__global__ void __launch_bounds__(32 * NW, rec_ctas_per_sm(TB, NT, NBUF) / NW > 0 ? rec_ctas_per_sm(TB, NT, NBUF) / NW : 1)
 k_lowpass_records(const float *__restrict__ e, u64 n, u64 ncorr, const __grid_constant__ LpTaps taps, SyncCtl *__restrict__ ctl,
-                  TileDesc *__restrict__ desc, Rec *__restrict__ pool, u32 pool_cap, u32 ntiles) {
+                  TileDesc *__restrict__ desc, Rec *__restrict__ pool, u32 pool_cap, u32 region, u32 ntiles) {
     constexpr int BOX = 2 * PW;
     constexpr int LOOK = 18 * BOX;
     constexpr int W = rec_tile_outputs(PW, TB);
@@ -117,12 +124,13 @@ k_lowpass_records(const float *__restrict__ e, u64 n, u64 ncorr, const __grid_co
     constexpr int WN = EOFF + 32;                           // window of one row, floats
     constexpr int LE = 32 * TB + EOFF;                      // staged e samples
     static_assert((LE + 31) / 32 <= TB + 2, "e rows");
-    static_assert((EOFF - (NT - 1)) % 2 == 0, "window pairs");
+    static_assert(EOFF - (NT - 1) >= 0 && EOFF + 31 + 1 < WN + 1, "window of a row");
     constexpr int PITCH = kRecRowPitch;
 
+    constexpr bool LOCK = NW > 1;
     extern __shared__ __align__(16) float rec_smem[];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *sbuf = rec_smem + warp * (2 * kRecSmemFloats);   // two buffers: the tile in work, the next tile's samples in flight
+    float *sbuf = rec_smem + warp * (NBUF * kRecSmemFloats);   // NBUF = 2: the tile in work, the next tile's samples in flight
 
     // e[i0 - EOFF, i0 + 32*TB) -> rows of `buf` (logical index m <-> e[i0 - EOFF + m]); samples with index < 1 or >= n are
     // zero (dsp.rs:399: signal[0] is never read).  Interior tiles: 16-byte cp.async, no registers, no waiting here.
@@ -149,20 +157,30 @@ k_lowpass_records(const float *__restrict__ e, u64 n, u64 ncorr, const __grid_co
         }
         cp_async_commit_group();
     };
-    auto ticket = [&]() {
-        u32 t = 0;
-        if (lane == 0) t = atomicAdd(&ctl->tile_ticket, 1u);
-        return __shfl_sync(0xffffffffu, t, 0);
+    // Tiles are dealt out statically (every tile costs the same): CTA b takes the tile groups b, b + gridDim.x, ...; a group
+    // is NW consecutive tiles, one per warp.  No tickets: two same-address atomics per tile (ticket + pool cursor, 11.7 k of
+    // them on one cache line) were what kept the first version at ~52 us whatever the occupancy.
+    auto phase_barrier = [&]() {
+        if (LOCK) __syncthreads();
     };
+    auto tile_of = [&](u32 it) { return (blockIdx.x + it * gridDim.x) * static_cast<u32>(NW) + warp; };
 
-    u32 tile = ticket();
+    // A warp whose tile lies beyond the last one (only in the last group, NW > 1) runs along on stale shared memory to keep
+    // the barriers simple; everything it would publish is gated by `active`.
+    u32 tile = tile_of(0);
     if (tile < ntiles) stage(tile, sbuf);
-    for (u32 it = 0; tile < ntiles; ++it) {
-        float *s = sbuf + (it & 1) * kRecSmemFloats;
-        const u32 next = ticket();
-        if (next < ntiles) stage(next, sbuf + ((it + 1) & 1) * kRecSmemFloats);
-        // the current tile's samples: everything but the group just committed
-        if (next < ntiles) asm volatile("cp.async.wait_group 1;" ::: "memory"); else cp_async_wait_all();
+    for (u32 it = 0; tile - (LOCK ? warp : 0u) < ntiles; ++it) {
+        const bool active = tile < ntiles;
+        const u32 next = tile_of(it + 1);
+        phase_barrier();
+        float *s = sbuf + (NBUF == 2 ? (it & 1) * kRecSmemFloats : 0);
+        if (NBUF == 2) {
+            if (next < ntiles) stage(next, sbuf + ((it + 1) & 1) * kRecSmemFloats);
+            // the current tile's samples: everything but the group just committed
+            if (next < ntiles) asm volatile("cp.async.wait_group 1;" ::: "memory"); else cp_async_wait_all();
+        } else {
+            cp_async_wait_all();
+        }
         __syncwarp();
         const u64 i0 = static_cast<u64>(tile) * W;
 
@@ -172,37 +190,35 @@ k_lowpass_records(const float *__restrict__ e, u64 n, u64 ncorr, const __grid_co
         for (int k = 0; k < BOX - 1; ++k) carry[k] = 0.f;
 #pragma unroll 1
         for (int rb = TB / 32 - 1; rb >= 0; --rb) {
+            phase_barrier();
             const u32 r = 32 * rb + lane;
             const float *row = s + r * PITCH;
-            f32x2 w2[WN / 2];
+            // One window sample x the taps of two neighbouring outputs: FFMA2 R.F32 (broadcast) x UR.pair + R.pair, the form that
+            // runs at 2.9 clk per sub-partition; the packed-window form (R.pair x UR.pair) used here before takes 5.0 clk
+            // and made this phase the kernel's bound (profiles/r02_fma_rate_bench.txt).
+            float w[WN];
 #pragma unroll
             for (int k = 0; k < WN / 4; ++k) {
                 const float4 q = *reinterpret_cast<const float4 *>(row + 4 * k + 4 * (k >> 3));
-                w2[2 * k] = pack2(q.x, q.y);
-                w2[2 * k + 1] = pack2(q.z, q.w);
+                w[4 * k] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
             }
             float fr[32 + BOX];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
+                f32x2 acc[8];
 #pragma unroll
-                for (int par = 0; par < 2; ++par) {
-                    f32x2 acc[8];
+                for (int v = 0; v < 8; ++v) acc[v] = 0ull;
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) acc[v] = 0ull;
-#pragma unroll
-                    for (int i = 0; i < NPAIR; ++i) {
-                        const float2 tp = par ? taps.a_odd[i] : taps.a_even[i];
-                        const f32x2 t2 = pack2(tp.x, tp.y);
-#pragma unroll
-                        for (int v = 0; v < 8; ++v) acc[v] = fma2(w2[EOFF / 2 + 8 * h + v - i], t2, acc[v]);
-                    }
+                for (int j = -1; j < NT; ++j) {
+                    const f32x2 t2 = pack2(taps.p[j + 1].x, taps.p[j + 1].y);   // (c[j], c[j+1]): outputs 2p and 2p+1 from sample EOFF+2p-j
 #pragma unroll
                     for (int v = 0; v < 8; ++v) {
-                        float lo, hi;
-                        unpack2(acc[v], lo, hi);
-                        fr[16 * h + par + 2 * v] = lo + hi;
+                        const float x = w[EOFF + 2 * (8 * h + v) - j];
+                        acc[v] = fma2(pack2(x, x), t2, acc[v]);
                     }
                 }
+#pragma unroll
+                for (int v = 0; v < 8; ++v) unpack2(acc[v], fr[16 * h + 2 * v], fr[16 * h + 2 * v + 1]);
             }
             // the first BOX-1 values of the next row: lane + 1, or (lane 31) the row block done before this one
 #pragma unroll
@@ -233,6 +249,7 @@ k_lowpass_records(const float *__restrict__ e, u64 n, u64 ncorr, const __grid_co
                 *reinterpret_cast<float4 *>(brow + 4 * k) = make_float4(b[4 * k], b[4 * k + 1], b[4 * k + 2], b[4 * k + 3]);
         }
         __syncwarp();
+        phase_barrier();
 
         // ---- phase 3: correlation, RD rounds of 32 items ----
         float c[RD][32];
@@ -244,6 +261,9 @@ k_lowpass_records(const float *__restrict__ e, u64 n, u64 ncorr, const __grid_co
             const u32 q = 32 * rd + lane;
             const u32 qa = q < NI ? q : NI - 1;             // idle lanes of the last round re-read the last item
             const float *brow = s + (qa + kRecShift) * PITCH;
+            // Packed adds (FFMA2 with an immediate +-1: 5.0 clk per warp instruction for 64 adds; scalar FADD would be 1.16 clk
+            // for 32) on purpose: the kernel is bound by instruction issue, not by the FMA pipe, and the scalar variant -- twice
+            // the instructions -- measured 6 us slower (profiles/r02_fma_rate_bench.txt).
             const f32x2 plus1 = pack2(1.f, 1.f), minus1 = pack2(-1.f, -1.f);
             f32x2 acc[16];
 #pragma unroll
@@ -287,6 +307,7 @@ k_lowpass_records(const float *__restrict__ e, u64 n, u64 ncorr, const __grid_co
             mx[rd] = fmaxf(fmaxf(gm[rd][0], gm[rd][1]), fmaxf(gm[rd][2], gm[rd][3]));
         }
 
+        phase_barrier();
         // ---- records: bounds from outside the lane by warp scans, then 8 independent chains of 8 per round ----
         float all[RD], pm[RD], sx[RD];
 #pragma unroll
@@ -342,51 +363,41 @@ k_lowpass_records(const float *__restrict__ e, u64 n, u64 ncorr, const __grid_co
             tot_s += ts;
             tot_p += tp;
         }
-        u32 base = 0;
-        if (lane == 0) base = atomicAdd(&ctl->pool_cursor, tot_s + tot_p);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const bool fits = static_cast<u64>(base) + tot_s + tot_p <= pool_cap;
-        // the correlation values go to the (dead) rows so that the records can be picked by a run-time index
-        __syncwarp();
-#pragma unroll
-        for (int rd = 0; rd < RD; ++rd) {
-            float *crow = s + (32 * rd + lane) * PITCH;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                *reinterpret_cast<float4 *>(crow + 4 * k) = make_float4(c[rd][4 * k], c[rd][4 * k + 1], c[rd][4 * k + 2], c[rd][4 * k + 3]);
+        // the tile's own region of the pool; only a tile with more than `region` records (long monotone stretches) takes its
+        // space from the shared overflow area behind the regions (region == 0: everything comes from there)
+        u32 base = tile * region;
+        if (tot_s + tot_p > region) {                       // warp-uniform
+            if (lane == 0 && active) base = ntiles * region + atomicAdd(&ctl->pool_cursor, tot_s + tot_p);
+            base = __shfl_sync(0xffffffffu, base, 0);
         }
-        __syncwarp();
+        const bool fits = active && static_cast<u64>(base) + tot_s + tot_p <= pool_cap;
+        phase_barrier();
         if (fits) {
-            // every lane writes its own records (a warp-cooperative, coalesced variant with a shuffle search per record
-            // measured 10 us slower: the lists are short and the shuffles are not free)
+            // Every lane writes its own records straight from the registers that hold its 32 correlation values: one
+            // predicated 8-byte store per (output, list), 128 per tile, all independent.  (The first version parked the values
+            // in shared memory and ran a `while (mask)` loop per lane -- find-first-set, LDS, store, a dependent chain whose
+            // trip count is the busiest lane's: a third of the kernel's time in the ncu source view.)
 #pragma unroll
             for (int rd = 0; rd < RD; ++rd) {
-                const float *crow = s + (32 * rd + lane) * PITCH;
                 const u32 p0 = static_cast<u32>(i0) + 32 * (32 * rd + lane);
-                u32 m = ms[rd], idx = base + os[rd];
-                while (m) {
-                    const u32 j = __ffs(m) - 1;
-                    m &= m - 1;
-                    pool[idx++] = Rec{p0 + j, crow[j]};
-                }
-                m = mp[rd];
-                idx = base + tot_s + op[rd];
-                while (m) {
-                    const u32 j = __ffs(m) - 1;
-                    m &= m - 1;
-                    pool[idx++] = Rec{p0 + j, crow[j]};
+                u32 is = base + os[rd], ip = base + tot_s + op[rd];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (ms[rd] & (1u << j)) { pool[is] = Rec{p0 + j, c[rd][j]}; ++is; }
+                    if (mp[rd] & (1u << j)) { pool[ip] = Rec{p0 + j, c[rd][j]}; ++ip; }
                 }
             }
         }
         float tmax = all[0];
 #pragma unroll
         for (int rd = 1; rd < RD; ++rd) tmax = fmaxf(tmax, all[rd]);
-        if (lane == 0) {
+        if (lane == 0 && active) {
             if (!fits) atomicExch(&ctl->overflow, 1u);
             desc[tile] = TileDesc{base, fits ? tot_s : 0u, fits ? tot_p : 0u, tmax};
         }
         __syncwarp();
         tile = next;
+        if (NBUF == 1 && tile < ntiles) stage(tile, sbuf);
     }
 }
 
@@ -395,7 +406,7 @@ k_lowpass_records(const float *__restrict__ e, u64 n, u64 ncorr, const __grid_co
 // are staged in shared memory; surviving roots go to root_list (ascending, at the tile's pool offset) and get dense ids
 // from an atomic cursor (ids are labels: any disjoint ranges do) -> tile_base[t], root position by id -> by_id.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kResolveThreads = 128;
+constexpr int kResolveThreads = 256;
 constexpr int kResolveCache = 192;               // records of one list kept in shared memory (longer lists: global); 21 KB per CTA: 10 CTAs per SM
 
 // first record of the ascending list L[0..np) whose value exceeds v; np if none
@@ -428,8 +439,11 @@ k_resolve_roots(const TileDesc *__restrict__ desc, const Rec *__restrict__ pool,
         if (blockIdx.x == 0 && threadIdx.x == 0) result->status = kSyncRedo;
         return;
     }
+    __shared__ u32 s_cnt[kResolveThreads / 32];
+    __shared__ u32 s_base;
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 t = blockIdx.x * (kResolveThreads / 32) + warp;
+    u32 cnt = 0, list_off = 0;
     if (t < ntiles) {
         // one parallel load: the descriptors of tiles t .. tlo+1 (a window starting in tile t ends in tile tlo or tlo+1)
         const u32 tlo = t + dist / tile_w;                  // (t*W + D) / W
@@ -471,7 +485,7 @@ k_resolve_roots(const TileDesc *__restrict__ desc, const Rec *__restrict__ pool,
         cp_async_commit_group();
         cp_async_wait_all();
         __syncwarp();
-        u32 cnt = 0;
+        list_off = d.off;
         const u32 tile_begin = t * tile_w;                  // correlation indices fit 32 bits (N_w < 2^32)
         const u32 last = static_cast<u32>(ncorr - 1);
         for (u32 c0 = 0; c0 < d.ns; c0 += 32) {
@@ -510,15 +524,26 @@ k_resolve_roots(const TileDesc *__restrict__ desc, const Rec *__restrict__ pool,
             }
             cnt += __popc(bal);
         }
-        u32 base = 0;
+    }
+    // dense ids: one atomic per CTA (its tiles take consecutive ranges) -- one per tile meant 5850 same-address atomics, all
+    // issued within the same few microseconds of a kernel that runs as a single wave
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 total = 0;
+#pragma unroll
+        for (int w = 0; w < kResolveThreads / 32; ++w) total += s_cnt[w];
+        s_base = total ? atomicAdd(&ctl->root_cursor, total) : 0u;
+    }
+    __syncthreads();
+    if (t < ntiles) {
+        u32 base = s_base;
+        for (u32 w = 0; w < warp; ++w) base += s_cnt[w];
         if (lane == 0) {
-            base = atomicAdd(&ctl->root_cursor, cnt);
             root_count[t] = cnt;
             tile_base[t] = base;
         }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        __syncwarp();
-        for (u32 k = lane; k < cnt; k += 32) by_id[base + k] = k < kResolveCache ? s_r[warp][k] : root_list[d.off + k];
+        for (u32 k = lane; k < cnt; k += 32) by_id[base + k] = k < kResolveCache ? s_r[warp][k] : root_list[list_off + k];
     }
     // seed of the peak list: first i <= D with corr[i] > 0.0 (decode.rs:208-209 + the else-if at :250) = the first
     // prefix record with a positive value
@@ -540,7 +565,6 @@ k_resolve_roots(const TileDesc *__restrict__ desc, const Rec *__restrict__ pool,
 // One CTA per half row: the e span of the half row sits in shared memory; a thread computes 4 consecutive pixels from
 // a 16-byte aligned window of its own.  Element 0 of the whole output is 0 (NoFilter never reads signal[0], dsp.rs:399).
 // ------------------------------------------------------------------------------------------------------------------
-struct LpFlat { float c[64]; };
 constexpr int kGatherLpThreads = 288;            // 2080 / 2 = 1040 pixels = 260 quads per half row
 
 __device__ __forceinline__ void cp_async4_zfill(float *dst, const float *src, bool valid) {
@@ -551,32 +575,71 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Persistent CTAs; the e span of the NEXT half row is copied into the other shared-memory buffer (4-byte cp.async: the
-// span starts at an arbitrary sample) while the current one is computed.
+// Four pixels of one thread: the window starts OFF samples into the 16-byte aligned floats at `src` (OFF = the row position's
+// alignment, compile time: the register indices are fixed per variant).  One window sample x the taps it has in two
+// neighbouring pixels (DEC samples apart): FFMA2 R.F32 (broadcast) x UR.pair + R.pair, NT + DEC of them per pixel pair --
+// half the instructions of the scalar form and 2.9 clk each (the packed-window form R.pair x UR.pair takes 5.0;
+// profiles/r02_fma_rate_bench.txt).
+template <int NT, int DEC, int OFF>
+__device__ __forceinline__ void gather_quad(const float *src, const LpTaps &lp, float (&acc)[4]) {
+    constexpr int EOFF = (NT - 1 + 3) / 4 * 4;
+    constexpr int WIN = (OFF + EOFF + 3 * DEC + 1 + 3) / 4 * 4;     // floats read for the 4 pixels
+    static_assert(EOFF - (NT - 1) >= 0 && OFF + EOFF + 3 * DEC < WIN && NT + DEC <= 72, "window");
+    float w[WIN];
+#pragma unroll
+    for (int k = 0; k < WIN / 4; ++k) {
+        const float4 q = *reinterpret_cast<const float4 *>(src + 4 * k);
+        w[4 * k] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
+    }
+    f32x2 acc2[2] = {0ull, 0ull};
+#pragma unroll
+    for (int j = -DEC; j < NT; ++j) {
+        const f32x2 t2 = pack2(lp.pd[j + DEC].x, lp.pd[j + DEC].y);   // (c[j], c[j+DEC])
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+            const float x = w[OFF + EOFF + DEC * (2 * pp) - j];       // tap j of pixel 2pp, tap j+DEC of pixel 2pp+1
+            acc2[pp] = fma2(pack2(x, x), t2, acc2[pp]);
+        }
+    }
+    unpack2(acc2[0], acc[0], acc[1]);
+    unpack2(acc2[1], acc[2], acc[3]);
+}
+
+// Persistent CTAs; the e span of the NEXT half row is copied into the other shared-memory buffer while the current one is
+// computed.  A row starts at an arbitrary sample, so the span is staged from the 16-byte aligned address below it (16-byte
+// cp.async: a quarter of the copy instructions of the first version, whose 4-byte copies kept the integer pipe busier than
+// the FMA pipe) and the remainder (0..3 samples) selects one of four compute variants.
 template <int NT, int DEC>
 __global__ void __launch_bounds__(kGatherLpThreads)
 k_gather_rows_lp(const float *__restrict__ e, u64 n, const u32 *__restrict__ positions, const SyncResult *__restrict__ result,
-                 u32 fixed_rows, u32 row, u32 px, const __grid_constant__ LpFlat lp, float *__restrict__ out) {
+                 u32 fixed_rows, u32 row, u32 px, const __grid_constant__ LpTaps lp, float *__restrict__ out) {
     constexpr int EOFF = (NT - 1 + 3) / 4 * 4;
-    constexpr int WIN = (EOFF + 3 * DEC + 1 + 3) / 4 * 4;      // floats a thread reads for its 4 pixels
     constexpr int PARTS = 2;
     extern __shared__ __align__(16) float g_smem[];
     const u32 n_rows = positions ? (result->status == 0 ? result->n_rows : 0u) : fixed_rows;
     const u32 part_px = (px / PARTS + 3) / 4 * 4;              // pixels per part (multiple of 4)
-    const u32 span = DEC * part_px + EOFF + 8;                  // staged samples per part
+    const u32 span = DEC * part_px + EOFF + 12;                 // staged samples per part (multiple of 4), incl. the alignment slack
     const u32 items = n_rows * PARTS;
     const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    auto stage = [&](u32 item, float *buf) {
+    const bool e_aligned = (reinterpret_cast<uintptr_t>(e) & 15) == 0;
+    // sample index of buf[0] of an item, and the offset of the row's window in it
+    auto origin = [&](u32 item, long long &a0) -> u32 {
         const u32 j = item / PARTS, part = item % PARTS;
         const u64 p = positions ? positions[j] : static_cast<u64>(j) * row;
-        const long long g0 = static_cast<long long>(p) + static_cast<long long>(DEC) * (part * part_px) - EOFF;   // sample at buf[0]
-        if (g0 >= 1 && static_cast<u64>(g0) + span <= n) {           // interior: no bounds to check
-            const float *src = e + g0;
-            for (u32 i = threadIdx.x; i < span; i += blockDim.x) cp_async4_zfill(buf + i, src + i, true);
+        const long long g0 = static_cast<long long>(p) + static_cast<long long>(DEC) * (part * part_px) - EOFF;
+        a0 = g0 & ~3ll;                                            // floor to a multiple of 4 (also for negative g0)
+        return static_cast<u32>(g0 - a0);
+    };
+    auto stage = [&](u32 item, float *buf) {
+        long long a0;
+        origin(item, a0);
+        if (e_aligned && a0 >= 4 && static_cast<u64>(a0) + span <= n) {    // interior: no bounds to check (sample 0 is not inside)
+            const float *src = e + a0;
+            for (u32 i = 4 * threadIdx.x; i < span; i += 4 * blockDim.x) cp_async16(buf + i, src + i);
         } else {
             for (u32 i = threadIdx.x; i < span; i += blockDim.x) {
-                const long long g = g0 + i;
-                const bool ok = g >= 1 && static_cast<u64>(g) < n;
+                const long long g = a0 + i;
+                const bool ok = g >= 1 && static_cast<u64>(g) < n;    // dsp.rs:399: signal[0] is never read
                 cp_async4_zfill(buf + i, ok ? e + g : e, ok);
             }
         }
@@ -591,21 +654,18 @@ k_gather_rows_lp(const float *__restrict__ e, u64 n, const u32 *__restrict__ pos
         cp_async_wait<1>();                                     // this thread's copies of the current buffer have landed
         __syncthreads();                                        // ... and everybody else's
         const u32 j = item / PARTS, part = item % PARTS;
+        long long a0;
+        const u32 off = origin(item, a0);                       // CTA-uniform
         const u32 c_begin = part * part_px;
         const u32 c_end = min(px, c_begin + part_px);
         for (u32 c4 = 4 * threadIdx.x; c_begin + c4 < c_end; c4 += 4 * blockDim.x) {
-            float w[WIN];
-            const float *src = cur + DEC * c4;                     // 16-byte aligned: DEC * c4 and span are multiples of 4
-#pragma unroll
-            for (int k = 0; k < WIN / 4; ++k) {
-                const float4 q = *reinterpret_cast<const float4 *>(src + 4 * k);
-                w[4 * k] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
-            }
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int jj = 0; jj < NT; ++jj) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) acc[u] = fmaf(w[EOFF + DEC * u - jj], lp.c[jj], acc[u]);
+            float acc[4];
+            const float *src = cur + DEC * c4;                  // 16-byte aligned: DEC * c4 and span are multiples of 4
+            switch (off) {
+            case 0: gather_quad<NT, DEC, 0>(src, lp, acc); break;
+            case 1: gather_quad<NT, DEC, 1>(src, lp, acc); break;
+            case 2: gather_quad<NT, DEC, 2>(src, lp, acc); break;
+            default: gather_quad<NT, DEC, 3>(src, lp, acc); break;
             }
             const u32 c = c_begin + c4;
             float *dst = out + static_cast<u64>(j) * px + c;

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "aptb200.h"
 #include "common.hpp"
@@ -250,6 +251,7 @@ int launch_lowpass_corr(const LaunchCtx &c, const float *e, u64 n, const float *
         t.a_even[i] = make_float2(tap(2 * i), tap(2 * i - 1));
         t.a_odd[i] = make_float2(tap(2 * i + 1), tap(2 * i));
     }
+    for (int j = -1; j < 63; ++j) t.p[j + 1] = make_float2(tap(j), tap(j + 1));
     const u64 ncorr = n > 38ull * pw ? n - 38ull * pw : 0;
     const u64 ntiles = (n + kLpTile - 1) / kLpTile;
     // persistent: exactly the resident CTAs, each walks its tiles with the next tile's loads in flight
@@ -373,13 +375,15 @@ int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, con
     return APT_OK;
 }
 
-static LpTaps make_lp_taps(const float *taps_host, u32 ntaps) {
+static LpTaps make_lp_taps(const float *taps_host, u32 ntaps, int dec = 0) {
     LpTaps t{};
     auto tap = [&](long long j) { return j >= 0 && j < static_cast<long long>(ntaps) ? taps_host[j] : 0.f; };
     for (int i = 0; i < 32; ++i) {
         t.a_even[i] = make_float2(tap(2 * i), tap(2 * i - 1));
         t.a_odd[i] = make_float2(tap(2 * i + 1), tap(2 * i));
     }
+    for (int j = -1; j < 63; ++j) t.p[j + 1] = make_float2(tap(j), tap(j + 1));
+    for (int j = -dec; j < 72 - dec; ++j) t.pd[j + dec] = make_float2(tap(j), tap(j + dec));
     return t;
 }
 
@@ -395,34 +399,48 @@ static int records_tb() {
 u32 records_tile(u32 pw) { return static_cast<u32>(rec_tile_outputs(static_cast<int>(pw), records_tb())); }
 
 int launch_lowpass_records(const LaunchCtx &c, const float *e, u64 n, u64 ncorr, const float *taps_host, u32 ntaps, u32 pw,
-                           SyncCtl *ctl, TileDesc *desc, Rec *pool, u32 pool_cap, u32 ntiles) {
+                           SyncCtl *ctl, TileDesc *desc, Rec *pool, u32 pool_cap, u32 region, u32 ntiles) {
     if (ntiles == 0) return APT_OK;
     const LpTaps t = make_lp_taps(taps_host, ntaps);
     const int tb = records_tb();
-    const size_t smem = 2ull * kRecWarps * rec_smem_floats(tb) * sizeof(float);
-    auto launch = [&](auto kern) {
-        if (smem > (48u << 10))      // per device, so not cached in the static below (only an experimental tile height gets here)
+    static const int nbuf = [] {
+        const char *e = getenv("APTB200_REC_NBUF");
+        return e && atoi(e) == 2 ? 2 : 1;
+    }();
+    auto launch = [&](auto kern, auto nwc) {
+        constexpr int NWc = decltype(nwc)::value;
+        const size_t smem = static_cast<size_t>(nbuf) * NWc * rec_smem_floats(tb) * sizeof(float);
+        if (smem > (48u << 10))      // the attribute is per device: set on every launch, not cached
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         static const int per_sm = [&] {
             int v = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, 32 * kRecWarps, smem) != cudaSuccess || v < 1) v = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, 32 * NWc, smem) != cudaSuccess || v < 1) v = 1;
             return v;
         }();
-        const unsigned want = (ntiles + kRecWarps - 1) / kRecWarps;
-        const unsigned grid = std::min<unsigned>(want, static_cast<unsigned>(c.sm_count) * per_sm);
-        kern<<<grid, 32 * kRecWarps, smem, c.stream>>>(e, n, ncorr, t, ctl, desc, pool, pool_cap, ntiles);
+        const unsigned want = (ntiles + NWc - 1) / NWc;
+        unsigned ctas = static_cast<unsigned>(per_sm);
+        static const int forced_w = [] { const char *e = getenv("APTB200_REC_WARPS"); return e ? atoi(e) : 0; }();
+        if (forced_w > 0) ctas = std::max(1u, std::min<unsigned>(static_cast<unsigned>(forced_w) / NWc, ctas));
+        const unsigned grid = std::min<unsigned>(want, static_cast<unsigned>(c.sm_count) * ctas);
+        kern<<<grid, 32 * NWc, smem, c.stream>>>(e, n, ncorr, t, ctl, desc, pool, pool_cap, region, ntiles);
     };
-    if (tb == 64) {
-        if (ntaps == 37 && pw == 3) launch(k_lowpass_records<37, 3, 64>);
-        else if (ntaps == 43 && pw == 4) launch(k_lowpass_records<43, 4, 64>);
-        else if (ntaps == 61 && pw == 5) launch(k_lowpass_records<61, 5, 64>);
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    auto pick = [&](auto tbc, auto nbc) -> int {
+        constexpr int TBc = decltype(tbc)::value, NBc = decltype(nbc)::value;
+        if (ntaps == 37 && pw == 3) {
+            launch(k_lowpass_records<37, 3, TBc, NBc>, I1{});
+        } else if (ntaps == 43 && pw == 4) launch(k_lowpass_records<43, 4, TBc, NBc>, I1{});
+        else if (ntaps == 61 && pw == 5) launch(k_lowpass_records<61, 5, TBc, NBc>, I1{});
         else return fail(APT_ERR_BAD_ARG, "no fused low-pass/record kernel for %u taps, pixel width %u", ntaps, pw);
-    } else {
-        if (ntaps == 37 && pw == 3) launch(k_lowpass_records<37, 3, 32>);
-        else if (ntaps == 43 && pw == 4) launch(k_lowpass_records<43, 4, 32>);
-        else if (ntaps == 61 && pw == 5) launch(k_lowpass_records<61, 5, 32>);
-        else return fail(APT_ERR_BAD_ARG, "no fused low-pass/record kernel for %u taps, pixel width %u", ntaps, pw);
-    }
+        return APT_OK;
+    };
+    using T32 = std::integral_constant<int, 32>;
+    using T64 = std::integral_constant<int, 64>;
+    int rc;
+    if (tb == 64) rc = nbuf == 2 ? pick(T64{}, I2{}) : pick(T64{}, I1{});
+    else rc = nbuf == 2 ? pick(T32{}, I2{}) : pick(T32{}, I1{});
+    if (rc != APT_OK) return rc;
     APT_CUDA(cudaGetLastError());
     return APT_OK;
 }
@@ -441,15 +459,27 @@ int launch_resolve_roots(const LaunchCtx &c, const TileDesc *desc, const Rec *po
 int launch_gather_lp(const LaunchCtx &c, const float *e, u64 n, const u32 *positions, const SyncResult *result,
                      u32 fixed_rows, u32 max_rows, u32 row, u32 px, u32 dec, const float *taps_host, u32 ntaps, float *out) {
     if (max_rows == 0) return APT_OK;
-    LpFlat lp{};
-    for (u32 i = 0; i < ntaps && i < 64; ++i) lp.c[i] = taps_host[i];
+    const LpTaps lp = make_lp_taps(taps_host, ntaps, static_cast<int>(dec));
     const u32 part_px = (px / 2 + 3) / 4 * 4;
     const u32 eoff = (ntaps - 1 + 3) / 4 * 4;
-    const size_t smem = 2 * (static_cast<size_t>(dec) * part_px + eoff + 8) * sizeof(float);   // double-buffered
-    const unsigned grid = static_cast<unsigned>(std::min<u64>(2ull * max_rows, static_cast<u64>(c.sm_count) * 4));
-    if (ntaps == 37 && dec == 3) k_gather_rows_lp<37, 3><<<grid, kGatherLpThreads, smem, c.stream>>>(e, n, positions, result, fixed_rows, row, px, lp, out);
-    else if (ntaps == 43 && dec == 4) k_gather_rows_lp<43, 4><<<grid, kGatherLpThreads, smem, c.stream>>>(e, n, positions, result, fixed_rows, row, px, lp, out);
-    else if (ntaps == 61 && dec == 5) k_gather_rows_lp<61, 5><<<grid, kGatherLpThreads, smem, c.stream>>>(e, n, positions, result, fixed_rows, row, px, lp, out);
+    const size_t smem = 2 * (static_cast<size_t>(dec) * part_px + eoff + 12) * sizeof(float);  // double-buffered (the kernel's `span`)
+    // persistent CTAs: exactly the resident ones (the register count decides: 3 per SM for 37 taps), and as many of those as
+    // give every CTA the same number of half rows
+    auto launch = [&](auto kern) {
+        static const int per_sm = [&] {
+            int v = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, kGatherLpThreads, smem) != cudaSuccess || v < 1) v = 1;
+            return v;
+        }();
+        const u64 items = 2ull * max_rows;
+        const u64 slots = static_cast<u64>(c.sm_count) * per_sm;
+        const u64 rounds = (items + slots - 1) / slots;
+        const unsigned grid = static_cast<unsigned>((items + rounds - 1) / rounds);
+        kern<<<grid, kGatherLpThreads, smem, c.stream>>>(e, n, positions, result, fixed_rows, row, px, lp, out);
+    };
+    if (ntaps == 37 && dec == 3) launch(k_gather_rows_lp<37, 3>);
+    else if (ntaps == 43 && dec == 4) launch(k_gather_rows_lp<43, 4>);
+    else if (ntaps == 61 && dec == 5) launch(k_gather_rows_lp<61, 5>);
     else return fail(APT_ERR_BAD_ARG, "no fused gather kernel for %u taps, decimation %u", ntaps, dec);
     static_assert(kGatherLpThreads * 4 >= 1040, "one pass of a half row");
     APT_CUDA(cudaGetLastError());

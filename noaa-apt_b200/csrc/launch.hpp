@@ -29,7 +29,7 @@ constexpr u32 kSyncRedo = 100;
 
 // Control block of the fused sync stage (kernels_sync2.cuh); zeroed at the start of every job.
 struct SyncCtl {
-    u32 tile_ticket;   // next tile of k_lowpass_records
+    u32 tile_ticket;   // (unused since the tiles of k_lowpass_records are dealt out statically)
     u32 pool_cursor;   // record-pool entries handed out
     u32 overflow;      // the pool was exhausted
     u32 root_cursor;   // dense root ids handed out by k_resolve_roots (= number of roots when it is done)
@@ -179,7 +179,7 @@ int launch_pick(const LaunchCtx &c, u64 ncorr, u64 nwork, u32 row, u32 dist, con
 // Fused sync stage (kernels_sync2.cuh): low-pass + correlation + per-tile records, then the roots; f and corr never reach HBM.
 u32 records_tile(u32 pixel_width);   // correlation positions per tile
 int launch_lowpass_records(const LaunchCtx &c, const float *e, u64 n, u64 ncorr, const float *taps_host, u32 ntaps,
-                           u32 pixel_width, SyncCtl *ctl, TileDesc *desc, Rec *pool, u32 pool_cap, u32 ntiles);
+                           u32 pixel_width, SyncCtl *ctl, TileDesc *desc, Rec *pool, u32 pool_cap, u32 region, u32 ntiles);
 int launch_resolve_roots(const LaunchCtx &c, const TileDesc *desc, const Rec *pool, u32 ntiles, u32 tile_w, u32 dist,
                          u64 ncorr, u32 *root_list, u32 *root_count, u32 *tile_base, u32 *by_id, SyncCtl *ctl,
                          SyncResult *result);
