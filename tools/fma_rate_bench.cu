@@ -8,6 +8,7 @@
 //   F  FFMA2  R(pair)  x (-1)     + R(pair)      packed add/subtract written as an FMA with an immediate (correlation signs)
 //   G  FADD2  R(pair)  + R(pair)                 packed add
 //   H  FADD   R + R                              scalar add
+//   I  FFMA2  R(pair)  x R(.F32)  + R(pair)      k_polyphase_ph (tap pair from shared memory x broadcast sample)
 // Each thread keeps 16 independent accumulator chains; one CTA per SM, W warps per CTA (W/4 per sub-partition); the
 // reported figure is cycles per warp-instruction per sub-partition (1.0 = one instruction per clock), and FMA/clk/SM.
 #include <cstdio>
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(1024, 1) k_rate(const __grid_constant__ Taps t
             if (FORM == 4) acc[i] = fmaf(x[i], r1[i & 3], acc[i]);
             if (FORM == 5) acc2[i] = fma2(x2[i], pack2(-1.f, -1.f), acc2[i]);
             if (FORM == 6) acc2[i] = add2(acc2[i], x2[i]);
+            if (FORM == 8) acc2[i] = fma2(x2[i], pack2(r1[i & 3], r1[i & 3]), acc2[i]);
             if (FORM == 7) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(acc[i]) : "f"(x[i]));
         }
     }
@@ -152,5 +154,6 @@ int main() {
     run<5>("F FFMA2 R.pair x (-1) + R.pair", 2, in, out, cyc, sms);
     run<6>("G FADD2 R.pair + R.pair", 2, in, out, cyc, sms);
     run<7>("H FADD  R + R", 1, in, out, cyc, sms);
+    run<8>("I FFMA2 R.pair x R.F32 (broadcast) + R.pair", 2, in, out, cyc, sms);
     return 0;
 }
