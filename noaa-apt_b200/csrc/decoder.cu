@@ -373,11 +373,13 @@ std::atomic<int> g_jobs_in_flight[64];      // per CUDA device: decodes submitte
 // The envelope e (4 N_w bytes, 45 MB for 15 min) is written by the resampler and read by the record and the gather
 // kernels; between those, the resampler's 173 MB input stream pushes most of it out of the 126 MB L2, so e goes to DRAM
 // and comes back (ncu in application order: 273 MB of DRAM traffic per decode against 188 MB algorithmic).  When this is the
-// only decode on the device, e gets a PERSISTING access-policy window on the decoder's stream (everything else the stream
-// touches is treated as streaming); with several decodes in flight the set-aside would only shrink the cache, so the
-// window is dropped.  APTB200_NO_L2_WINDOW=1 disables it.
+// only decode on the device, e can get a PERSISTING access-policy window on the decoder's stream (everything else the
+// stream touches is treated as streaming): 201 MB per decode, same speed (the kernels that read e are not memory bound).
+// With several decodes in flight the set-aside would only shrink the cache, so the window is dropped then.
+// OPT-IN (APTB200_L2_WINDOW=1): measured on one GPU only; the 4-GPU run that would have validated it next to NCCL and in
+// a multi-device process did not complete, and a device-wide L2 carve-out is not something to switch on unverified.
 static void set_envelope_l2_window(apt_decoder *d, uint64_t nwork, bool alone) {
-    static const bool disabled = getenv("APTB200_NO_L2_WINDOW") != nullptr;
+    static const bool disabled = getenv("APTB200_L2_WINDOW") == nullptr;
     static std::atomic<int> setaside[64];              // per device: bytes set aside (0 not tried yet, -1 unsupported)
     static std::atomic<int> window_max[64];            // per device: largest access-policy window
     if (disabled || d->device < 0 || d->device >= 64 || !d->d_e) return;
