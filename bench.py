@@ -467,7 +467,7 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- the single-recording configuration (configs[1]) and the other input rates, measured in the same run ----
     single, rates = None, None
-    if not args.no_extras and args.workload == "c4":
+    if not args.no_extras and args.workload == "c4" and world == 1:      # N = 1 only: the N > 1 line is the batch workload alone
         def one_device():
             dec.submit_device(x_devs[0].data_ptr(), F32, n, True, out_devs[0].data_ptr(), bound)
             dec.wait()
@@ -478,8 +478,7 @@ def run_b200(args, rank, local_rank, world):
         _, s_tot = throughput(n * K, s_ms)
         single = {"workload": "single synthetic 48000 Hz 900-s recording per GPU (BASELINE configs[1]), one decode at a time",
                   "value": world * n * K / (s_tot * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": s_tot / K}
-        if world == 1:
-            rates = other_rates(na, lib, cset, local_rank, timed, K)
+        rates = other_rates(na, lib, cset, local_rank, timed, K)
 
     # ---- parity of what was timed: rows and sync positions against the CPU oracle (outside the timed regions) ----
     # Sync positions must be the oracle's.  The one tolerated exception is a TIE: the picker compares correlation values
