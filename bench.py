@@ -278,7 +278,8 @@ def run_b200(args, rank, local_rank, world):
     dist_on = world > 1
     dist = None
     if dist_on:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
+        # NCCL prints its "NCCL version ..." banner on STDOUT at NCCL_DEBUG >= VERSION (WARN included): leave the variable
+        # alone if the caller set it, do not set it otherwise -- and the JSON line is the LAST line of stdout either way
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
