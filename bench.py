@@ -638,10 +638,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # Watchdog: a default run takes 2-4 minutes.  If a rank is still here after 15 (longer for many steps), every thread's
+    # Python stack goes to stderr and the process exits non-zero -- a hang then costs minutes and leaves evidence instead of
+    # holding the box until an outer timeout kills it without any.
+    import faulthandler
+    faulthandler.dump_traceback_later(max(900, 40 * (args.steps + args.warmup)), exit=True)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_b200(args, rank, local_rank, world)
+    faulthandler.cancel_dump_traceback_later()
 
 
 if __name__ == "__main__":
