@@ -173,6 +173,7 @@ def make_recording(rate, seconds, seed):
 
 
 def make_recordings(rate, seconds, seeds):
+    from noaa_apt_b200 import synth  # noqa: F401  -- first import on THIS thread: the import shim swaps sys.modules entries
     with ThreadPoolExecutor(max_workers=len(seeds)) as ex:
         return list(ex.map(lambda s: make_recording(rate, seconds, s), seeds))
 
