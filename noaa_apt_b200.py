@@ -9,17 +9,5 @@ _dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "noaa-apt_b200")
 _spec = importlib.util.spec_from_file_location(
     "noaa_apt_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
 _mod = importlib.util.module_from_spec(_spec)
-# Other threads that import the package while it is still executing must WAIT for it (on this shim's module lock, which
-# the importing thread holds), not pick up a half-initialised module: mark it the way importlib marks a module it loads.
-try:
-    _spec._initializing = True
-except Exception:
-    pass
 sys.modules["noaa_apt_b200"] = _mod
-try:
-    _spec.loader.exec_module(_mod)
-finally:
-    try:
-        _spec._initializing = False
-    except Exception:
-        pass
+_spec.loader.exec_module(_mod)
