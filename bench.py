@@ -639,11 +639,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # Watchdog: a default run takes 2-4 minutes.  If a rank is still here after 15 (longer for many steps), every thread's
-    # Python stack goes to stderr and the process exits non-zero -- a hang then costs minutes and leaves evidence instead of
-    # holding the box until an outer timeout kills it without any.
+    # Watchdog: a default run takes 2-4 minutes.  If a rank is still here after 13 (longer for many steps; the driver's own
+    # limit per run was 870 s in round 1), every thread's Python stack goes to stderr and the process exits non-zero -- a
+    # hang then leaves evidence instead of being killed from outside without any.
     import faulthandler
-    faulthandler.dump_traceback_later(max(900, 40 * (args.steps + args.warmup)), exit=True)
+    total_steps = args.steps + args.warmup
+    faulthandler.dump_traceback_later(780 if total_steps <= 40 else 20 * total_steps, exit=True)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
